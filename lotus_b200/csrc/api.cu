@@ -1,0 +1,470 @@
+// api.cu — the C-ABI of libb2lotus.so (include/lotus_b200.h): handles, workspaces and the search pipeline
+//   prep queries -> tcgen05 filter (knn_filter_sm100.cu) -> finalize/certify (knn_exact.cu) -> dense exact
+//   fallback for uncertified queries.
+// Reference call sites replaced: lotus/vector_store/faiss_vs.py:22-77 (see the header for the mapping).
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b2 {
+
+static thread_local std::string g_err;
+int64_t g_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return B2_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+            p = nullptr;
+            return B2_ENOMEM;
+        }
+        cap = want;
+        return B2_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct HostBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return B2_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes + 256);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("cudaMallocHost(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+            return B2_ENOMEM;
+        }
+        cap = bytes + 256;
+        return B2_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace b2
+
+using namespace b2;
+
+struct b2_index {
+    int device = 0;
+    int64_t n = 0;
+    int32_t d = 0;
+    int32_t dtype = B2_F32;
+    int32_t metric = B2_METRIC_IP;
+    DevBuf store, filt_pad, norm2, scalar;
+    MatView view;
+    // per-call workspaces
+    DevBuf q_in, q_filt, cand_score, cand_id, cand_thr, flags, sel, dense, out_sc, out_id, ids_dev;
+    DevBuf sub_store, sub_filt, sub_norm2;
+    HostBuf h_flags;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_filter_ms = -1.f;
+};
+
+namespace b2 {
+
+static size_t esize(int dtype) { return dtype == B2_F32 ? 4 : 2; }
+
+// Build the searchable view of a row-major matrix that already sits in device memory.
+static int build_view(const void* store, int64_t n, int d, int dtype, DevBuf& filt_pad, DevBuf& norm2, DevBuf& scalar,
+                      MatView& v, cudaStream_t st) {
+    v.store = store;
+    v.n = n;
+    v.d = d;
+    v.dtype = dtype;
+    const int align = dtype == B2_F32 ? 4 : 8;  // TMA row pitch must be a multiple of 16 bytes
+    if (d % align == 0) {
+        v.filt = store;
+        v.filt_pitch = d;
+    } else {
+        v.filt_pitch = round_up(d, align);
+        B2_TRY(filt_pad.ensure((size_t)std::max<int64_t>(n, 1) * v.filt_pitch * esize(dtype)));
+        B2_TRY(launch_convert_pad(store, dtype, n, d, filt_pad.p, dtype, v.filt_pitch, st));
+        v.filt = filt_pad.p;
+    }
+    B2_TRY(norm2.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(float)));
+    B2_TRY(scalar.ensure(64));
+    B2_TRY(launch_row_norms(store, dtype, n, d, norm2.as<float>(), scalar.as<float>(), st));
+    float mx = 0.f;
+    B2_CUDA(cudaMemcpyAsync(&mx, scalar.p, sizeof(float), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    v.norm2 = norm2.as<float>();
+    v.max_norm = mx;
+    return B2_OK;
+}
+
+// relative (to ||q||*||x||) bound on |filter score - exact score| of the inner product
+static float filter_rel_eps(int index_dtype, int q_dtype, int d) {
+    // fp32 accumulation inside the tensor core: products are exact, every accumulation step may lose one
+    // (truncated) ulp of the running magnitude; (d + 64) * 2^-23 is generous (validated in tests/test_gpu_filter.py)
+    double acc = (double)(d + 64) * 1.1920929e-7;
+    double conv = 0.0;
+    if (index_dtype == B2_F32) {
+        conv = 2.0 * 9.765625e-4 + 1e-6;  // both operands truncated to TF32 (10 explicit mantissa bits)
+    } else if (q_dtype == B2_F32) {
+        conv = 3.90625e-3 + 1e-6;  // queries rounded to bf16 for the filter (index values are exact)
+    }
+    return (float)(acc + conv);
+}
+
+__global__ void fill_pad_kernel(float* sc, int64_t* id, int64_t total, float pad) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        sc[t] = pad;
+        id[t] = -1;
+    }
+}
+
+static int search_core(b2_index* idx, const MatView& X, const void* q_dev, int q_dtype, int64_t nq, int k,
+                       const int64_t* id_map, int64_t id_offset, float* out_sc, int64_t* out_id, cudaStream_t st) {
+    idx->last_filter_ms = -1.f;
+    if (nq <= 0) return B2_OK;
+    g_stats[ST_QUERIES] += nq;
+    const int metric = idx->metric;
+    if (X.n <= 0) {
+        fill_pad_kernel<<<148, 256, 0, st>>>(out_sc, out_id, nq * k, metric == B2_METRIC_L2 ? FLT_MAX : -FLT_MAX);
+        B2_LAUNCH_CHECK();
+        return B2_OK;
+    }
+    const int kp = filter_kp_for_k(k);
+    const bool use_filter = kp != 0 && X.n >= 512;
+    const int64_t dense_rows_cap = std::max<int64_t>(1, (int64_t)(256ull << 20) / (X.n * 4));
+    if (!use_filter) {
+        if (k > dense_max_k()) {
+            set_error("k=%d is not supported (max %d)", k, dense_max_k());
+            return B2_ERANGE;
+        }
+        const int64_t rows = std::min<int64_t>(dense_rows_cap, nq);
+        B2_TRY(idx->dense.ensure((size_t)rows * X.n * sizeof(float)));
+        B2_TRY(launch_dense_topk(X, q_dev, q_dtype, nq, nullptr, nq, metric, k, id_map, id_offset, idx->dense.as<float>(), rows,
+                                 out_sc, out_id, st));
+        g_stats[ST_FALLBACK] += nq;
+        return B2_OK;
+    }
+    int dev_sms = 148;
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, idx->device);
+    const int filt_dtype = X.dtype;
+    const int64_t q_pitch = round_up(X.d, filt_dtype == B2_F32 ? 4 : 8);
+    const float rel_eps = filter_rel_eps(X.dtype, q_dtype, X.d);
+    // bound the candidate workspace: process the queries in chunks
+    const int64_t chunk = 1 << 20;
+    for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
+        const int64_t nqc = std::min<int64_t>(chunk, nq - q0);
+        const char* qc = reinterpret_cast<const char*>(q_dev) + (size_t)q0 * X.d * esize(q_dtype);
+        float* osc = out_sc + (size_t)q0 * k;
+        int64_t* oid = out_id + (size_t)q0 * k;
+        const int n_splits = filter_choose_splits(nqc, X.n, dev_sms);
+        B2_TRY(idx->q_filt.ensure((size_t)nqc * q_pitch * esize(filt_dtype)));
+        B2_TRY(idx->cand_score.ensure((size_t)nqc * n_splits * kp * sizeof(float)));
+        B2_TRY(idx->cand_id.ensure((size_t)nqc * n_splits * kp * sizeof(int32_t)));
+        B2_TRY(idx->cand_thr.ensure((size_t)nqc * n_splits * sizeof(float)));
+        B2_TRY(idx->flags.ensure((size_t)nqc * sizeof(int32_t)));
+        B2_TRY(idx->h_flags.ensure((size_t)nqc * sizeof(int32_t)));
+        B2_TRY(launch_prep_queries(qc, q_dtype, nqc, X.d, idx->q_filt.p, filt_dtype, q_pitch, st));
+        B2_CUDA(cudaEventRecord(idx->ev0, st));
+        B2_TRY(launch_knn_filter(X, idx->q_filt.p, q_pitch, nqc, metric, kp, n_splits, idx->cand_score.as<float>(),
+                                 idx->cand_id.as<int32_t>(), idx->cand_thr.as<float>(), idx->device, st));
+        B2_CUDA(cudaEventRecord(idx->ev1, st));
+        B2_TRY(launch_finalize(X, qc, q_dtype, nqc, metric, k, kp, n_splits, idx->cand_score.as<float>(),
+                               idx->cand_id.as<int32_t>(), idx->cand_thr.as<float>(), rel_eps, id_map, id_offset, osc, oid,
+                               idx->flags.as<int32_t>(), st));
+        B2_CUDA(cudaMemcpyAsync(idx->h_flags.p, idx->flags.p, (size_t)nqc * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        cudaError_t se = cudaStreamSynchronize(st);
+        if (se != cudaSuccess) {
+            set_error("search pipeline failed on the device: %s", cudaGetErrorString(se));
+            return B2_ECUDA;
+        }
+        float ms = -1.f;
+        if (cudaEventElapsedTime(&ms, idx->ev0, idx->ev1) == cudaSuccess)
+            idx->last_filter_ms = (idx->last_filter_ms < 0 ? 0.f : idx->last_filter_ms) + ms;
+        // exact fallback for the queries the certificate could not cover
+        const int32_t* hf = reinterpret_cast<const int32_t*>(idx->h_flags.p);
+        std::vector<int32_t> sel;
+        for (int64_t i = 0; i < nqc; ++i)
+            if (hf[i]) sel.push_back((int32_t)i);
+        if (!sel.empty()) {
+            if (k > dense_max_k()) {
+                set_error("internal: fallback with k=%d", k);
+                return B2_ERANGE;
+            }
+            g_stats[ST_FALLBACK] += (int64_t)sel.size();
+            B2_TRY(idx->sel.ensure(sel.size() * sizeof(int32_t)));
+            B2_CUDA(cudaMemcpyAsync(idx->sel.p, sel.data(), sel.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            const int64_t rows = std::min<int64_t>(dense_rows_cap, (int64_t)sel.size());
+            B2_TRY(idx->dense.ensure((size_t)rows * X.n * sizeof(float)));
+            B2_TRY(launch_dense_topk(X, qc, q_dtype, nqc, idx->sel.as<int32_t>(), (int64_t)sel.size(), metric, k, id_map,
+                                     id_offset, idx->dense.as<float>(), rows, osc, oid, st));
+            B2_CUDA(cudaStreamSynchronize(st));  // `sel` (host vector) must outlive the copy
+        }
+    }
+    return B2_OK;
+}
+
+// searchable view for an ids subset (faiss_vs.py:57-64: temporary index over vecs[ids])
+static int build_subset(b2_index* idx, const int64_t* ids_dev, int64_t m, MatView& sub, cudaStream_t st) {
+    B2_TRY(idx->sub_store.ensure((size_t)std::max<int64_t>(m, 1) * idx->d * esize(idx->dtype)));
+    B2_TRY(idx->scalar.ensure(64));
+    int* err = reinterpret_cast<int*>(idx->scalar.as<char>() + 16);
+    B2_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
+    B2_TRY(launch_gather_rows(idx->store.p, idx->dtype, idx->d, ids_dev, m, idx->n, idx->sub_store.p, err, st));
+    int herr = 0;
+    B2_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    if (herr) {
+        set_error("ids contains a position outside [0, %lld)", (long long)idx->n);
+        return B2_ERANGE;
+    }
+    return build_view(idx->sub_store.p, m, idx->d, idx->dtype, idx->sub_filt, idx->sub_norm2, idx->scalar, sub, st);
+}
+
+}  // namespace b2
+
+// =====================================================================================================================
+extern "C" {
+
+int b2_abi_version(void) { return B2_ABI_VERSION; }
+const char* b2_last_error(void) { return g_err.c_str(); }
+
+int b2_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        int major = 0;
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i);
+        if (major == 10) ok++;
+    }
+    return ok;
+}
+
+int b2_max_k(void) { return dense_max_k(); }
+
+int b2_index_create(const void* x, int64_t n, int32_t d, int32_t dtype, int32_t metric, int32_t device, int32_t x_on_device,
+                    b2_index** out) {
+    if (!out) { set_error("out is NULL"); return B2_EINVAL; }
+    *out = nullptr;
+    if (n < 0 || d <= 0 || (n > 0 && !x)) { set_error("bad matrix shape n=%lld d=%d", (long long)n, d); return B2_EINVAL; }
+    if (dtype != B2_F32 && dtype != B2_BF16) { set_error("dtype must be B2_F32 or B2_BF16"); return B2_EINVAL; }
+    if (metric != B2_METRIC_IP && metric != B2_METRIC_L2) { set_error("metric must be B2_METRIC_IP or B2_METRIC_L2"); return B2_EINVAL; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device: libb2lotus has no CPU fallback");
+        return B2_ENODEV;
+    }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (%d visible)", device, ndev); return B2_EINVAL; }
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (major != 10) { set_error("device %d is sm_%d0; this library is built for sm_100a (B200) only", device, major); return B2_ENODEV; }
+    DeviceGuard guard(device);
+    b2_index* idx = new b2_index();
+    idx->device = device;
+    idx->n = n;
+    idx->d = d;
+    idx->dtype = dtype;
+    idx->metric = metric;
+    auto fail = [&](int rc) { b2_index_free(idx); return rc; };
+    if (cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&idx->ev0) != cudaSuccess || cudaEventCreate(&idx->ev1) != cudaSuccess) {
+        set_error("stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(B2_ECUDA);
+    }
+    const size_t bytes = (size_t)std::max<int64_t>(n, 1) * d * esize(dtype);
+    int rc = idx->store.ensure(bytes);
+    if (rc != B2_OK) return fail(rc);
+    if (n > 0) {
+        cudaError_t e = cudaMemcpyAsync(idx->store.p, x, (size_t)n * d * esize(dtype),
+                                        x_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, idx->stream);
+        if (e != cudaSuccess) { set_error("copy of the matrix failed: %s", cudaGetErrorString(e)); return fail(B2_ECUDA); }
+    }
+    rc = build_view(idx->store.p, n, d, dtype, idx->filt_pad, idx->norm2, idx->scalar, idx->view, idx->stream);
+    if (rc != B2_OK) return fail(rc);
+    *out = idx;
+    return B2_OK;
+}
+
+void b2_index_free(b2_index* idx) {
+    if (!idx) return;
+    DeviceGuard guard(idx->device);
+    DevBuf* bufs[] = {&idx->store, &idx->filt_pad, &idx->norm2, &idx->scalar, &idx->q_in, &idx->q_filt, &idx->cand_score,
+                      &idx->cand_id, &idx->cand_thr, &idx->flags, &idx->sel, &idx->dense, &idx->out_sc, &idx->out_id,
+                      &idx->ids_dev, &idx->sub_store, &idx->sub_filt, &idx->sub_norm2};
+    for (DevBuf* b : bufs) b->release();
+    idx->h_flags.release();
+    if (idx->ev0) cudaEventDestroy(idx->ev0);
+    if (idx->ev1) cudaEventDestroy(idx->ev1);
+    if (idx->stream) cudaStreamDestroy(idx->stream);
+    delete idx;
+}
+
+int64_t b2_index_ntotal(const b2_index* idx) { return idx ? idx->n : -1; }
+int32_t b2_index_dim(const b2_index* idx) { return idx ? idx->d : -1; }
+int32_t b2_index_dtype(const b2_index* idx) { return idx ? idx->dtype : -1; }
+int32_t b2_index_metric(const b2_index* idx) { return idx ? idx->metric : -1; }
+int32_t b2_index_device(const b2_index* idx) { return idx ? idx->device : -1; }
+const void* b2_index_data_dev(const b2_index* idx) { return idx ? idx->store.p : nullptr; }
+float b2_last_filter_ms(const b2_index* idx) { return idx ? idx->last_filter_ms : -1.f; }
+
+static int check_search_args(b2_index* idx, const void* q, int64_t nq, int32_t q_dtype, int32_t k) {
+    if (!idx) { set_error("Index not loaded"); return B2_EINVAL; }
+    if (nq < 0 || (nq > 0 && !q)) { set_error("bad query batch"); return B2_EINVAL; }
+    if (q_dtype != B2_F32 && q_dtype != B2_BF16) { set_error("q_dtype must be B2_F32 or B2_BF16"); return B2_EINVAL; }
+    if (k <= 0) { set_error("k must be positive (got %d)", k); return B2_EINVAL; }
+    if (k > dense_max_k()) { set_error("k=%d is not supported (max %d)", k, dense_max_k()); return B2_ERANGE; }
+    return B2_OK;
+}
+
+int b2_index_search_dev(b2_index* idx, const void* q_dev, int64_t nq, int32_t q_dtype, int32_t k, const int64_t* ids_dev,
+                        int64_t n_ids, int64_t id_offset, float* out_scores_dev, int64_t* out_idx_dev, void* stream) {
+    B2_TRY(check_search_args(idx, q_dev, nq, q_dtype, k));
+    if (nq == 0) return B2_OK;
+    if (!out_scores_dev || !out_idx_dev) { set_error("output buffers are NULL"); return B2_EINVAL; }
+    DeviceGuard guard(idx->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (ids_dev) {
+        if (n_ids < 0) { set_error("n_ids < 0"); return B2_EINVAL; }
+        MatView sub;
+        B2_TRY(build_subset(idx, ids_dev, n_ids, sub, st));
+        B2_TRY(search_core(idx, sub, q_dev, q_dtype, nq, k, ids_dev, 0, out_scores_dev, out_idx_dev, st));
+    } else {
+        B2_TRY(search_core(idx, idx->view, q_dev, q_dtype, nq, k, nullptr, id_offset, out_scores_dev, out_idx_dev, st));
+    }
+    B2_CUDA(cudaStreamSynchronize(st));
+    return B2_OK;
+}
+
+int b2_index_search(b2_index* idx, const void* q, int64_t nq, int32_t q_dtype, int32_t k, const int64_t* ids, int64_t n_ids,
+                    float* out_scores, int64_t* out_idx) {
+    B2_TRY(check_search_args(idx, q, nq, q_dtype, k));
+    if (nq == 0) return B2_OK;
+    if (!out_scores || !out_idx) { set_error("output buffers are NULL"); return B2_EINVAL; }
+    DeviceGuard guard(idx->device);
+    cudaStream_t st = idx->stream;
+    const size_t qbytes = (size_t)nq * idx->d * esize(q_dtype);
+    B2_TRY(idx->q_in.ensure(qbytes));
+    B2_TRY(idx->out_sc.ensure((size_t)nq * k * sizeof(float)));
+    B2_TRY(idx->out_id.ensure((size_t)nq * k * sizeof(int64_t)));
+    B2_CUDA(cudaMemcpyAsync(idx->q_in.p, q, qbytes, cudaMemcpyHostToDevice, st));
+    const int64_t* ids_dev = nullptr;
+    if (ids) {
+        if (n_ids < 0) { set_error("n_ids < 0"); return B2_EINVAL; }
+        bool identity = n_ids == idx->n;
+        for (int64_t i = 0; identity && i < n_ids; ++i) identity = ids[i] == i;
+        if (!identity) {
+            B2_TRY(idx->ids_dev.ensure((size_t)std::max<int64_t>(n_ids, 1) * sizeof(int64_t)));
+            B2_CUDA(cudaMemcpyAsync(idx->ids_dev.p, ids, (size_t)n_ids * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+            ids_dev = idx->ids_dev.as<int64_t>();
+        }
+    }
+    if (ids_dev) {
+        MatView sub;
+        B2_TRY(build_subset(idx, ids_dev, n_ids, sub, st));
+        B2_TRY(search_core(idx, sub, idx->q_in.p, q_dtype, nq, k, ids_dev, 0, idx->out_sc.as<float>(), idx->out_id.as<int64_t>(), st));
+    } else {
+        B2_TRY(search_core(idx, idx->view, idx->q_in.p, q_dtype, nq, k, nullptr, 0, idx->out_sc.as<float>(),
+                           idx->out_id.as<int64_t>(), st));
+    }
+    B2_CUDA(cudaMemcpyAsync(out_scores, idx->out_sc.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaMemcpyAsync(out_idx, idx->out_id.p, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { set_error("search failed on the device: %s", cudaGetErrorString(e)); return B2_ECUDA; }
+    return B2_OK;
+}
+
+int b2_merge_topk_dev(const float* scores_dev, const int64_t* idx_dev, int32_t g, int64_t nq, int32_t k, int32_t metric,
+                      int32_t device, float* out_scores_dev, int64_t* out_idx_dev, void* stream) {
+    if (g <= 0 || k <= 0 || nq < 0) { set_error("bad merge shape g=%d nq=%lld k=%d", g, (long long)nq, k); return B2_EINVAL; }
+    if (nq == 0) return B2_OK;
+    if (!scores_dev || !idx_dev || !out_scores_dev || !out_idx_dev) { set_error("NULL buffer"); return B2_EINVAL; }
+    DeviceGuard guard(device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    B2_TRY(launch_merge_topk(scores_dev, idx_dev, g, nq, k, metric, out_scores_dev, out_idx_dev, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    return B2_OK;
+}
+
+int b2_index_gather(b2_index* idx, const int64_t* ids, int64_t m, void* out, int32_t out_on_device) {
+    if (!idx) { set_error("Index not loaded"); return B2_EINVAL; }
+    if (m < 0 || (m > 0 && (!ids || !out))) { set_error("bad gather arguments"); return B2_EINVAL; }
+    if (m == 0) return B2_OK;
+    DeviceGuard guard(idx->device);
+    cudaStream_t st = idx->stream;
+    const size_t row_bytes = (size_t)idx->d * esize(idx->dtype);
+    B2_TRY(idx->scalar.ensure(64));
+    int* err = reinterpret_cast<int*>(idx->scalar.as<char>() + 16);
+    B2_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
+    const int64_t* ids_dev = ids;
+    void* out_dev = out;
+    if (!out_on_device) {
+        B2_TRY(idx->ids_dev.ensure((size_t)m * sizeof(int64_t)));
+        B2_CUDA(cudaMemcpyAsync(idx->ids_dev.p, ids, (size_t)m * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        ids_dev = idx->ids_dev.as<int64_t>();
+        B2_TRY(idx->sub_store.ensure((size_t)m * row_bytes));
+        out_dev = idx->sub_store.p;
+    }
+    B2_TRY(launch_gather_rows(idx->store.p, idx->dtype, idx->d, ids_dev, m, idx->n, out_dev, err, st));
+    int herr = 0;
+    B2_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (!out_on_device) B2_CUDA(cudaMemcpyAsync(out, out_dev, (size_t)m * row_bytes, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    if (herr) { set_error("ids contains a position outside [0, %lld)", (long long)idx->n); return B2_ERANGE; }
+    return B2_OK;
+}
+
+int b2_stats(int64_t* out, int32_t cap) {
+    int n = cap < 8 ? cap : 8;
+    for (int i = 0; i < n; ++i) out[i] = g_stats[i];
+    return n;
+}
+void b2_stats_reset(void) { memset(g_stats, 0, sizeof(g_stats)); }
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// common.cuh — shared declarations for libb2lotus.so (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/lotus_b200.h"
+
+namespace b2 {
+
+// ---- error plumbing ------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern int64_t g_stats[8];
+enum { ST_LAUNCHES = 0, ST_QUERIES = 1, ST_FALLBACK = 2, ST_FILTER_LAUNCHES = 3, ST_RESCORED = 4 };
+
+#define B2_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            b2::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return B2_ECUDA;                                                                       \
+        }                                                                                          \
+    } while (0)
+
+#define B2_LAUNCH_CHECK()                                                                          \
+    do {                                                                                           \
+        b2::g_stats[b2::ST_LAUNCHES]++;                                                            \
+        cudaError_t _e = cudaGetLastError();                                                       \
+        if (_e != cudaSuccess) {                                                                   \
+            b2::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return B2_ECUDA;                                                                       \
+        }                                                                                          \
+    } while (0)
+
+#define B2_TRY(expr)            \
+    do {                        \
+        int _rc = (expr);       \
+        if (_rc != B2_OK) return _rc; \
+    } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+// ---- order-preserving keys --------------------------------------------------------------------------------
+// ord(f) is monotone in f (for non-NaN f); -0.0 is folded onto +0.0 first.
+__host__ __device__ __forceinline__ uint32_t f32_ord(float f) {
+    f = f + 0.0f;
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, 4);
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float f32_unord(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+// "best first when sorted ascending": IP wants large scores first, L2 small distances first.
+__host__ __device__ __forceinline__ uint32_t best_first_key(float s, int metric) {
+    uint32_t o = f32_ord(s);
+    return metric == B2_METRIC_IP ? ~o : o;
+}
+__host__ __device__ __forceinline__ float best_first_unkey(uint32_t k, int metric) {
+    return f32_unord(metric == B2_METRIC_IP ? ~k : k);
+}
+
+// ---- a matrix the kernels can search ---------------------------------------------------------------------
+// `store` holds the exact values (dtype f32 or bf16, row pitch `d`). `filt` is what the tcgen05 filter
+// streams through TMA: bf16 (pitch multiple of 8 elements) for a bf16 index, fp32 (pitch multiple of 4)
+// read as TF32 for an fp32 index; it aliases `store` whenever the pitch already qualifies.
+struct MatView {
+    const void* store = nullptr;
+    const void* filt = nullptr;
+    const float* norm2 = nullptr;  // [n] fp32 squared norms of the exact rows (L2 filter epilogue)
+    int64_t n = 0;
+    int32_t d = 0;
+    int32_t dtype = B2_F32;
+    int64_t filt_pitch = 0;  // elements
+    float max_norm = 0.f;    // max_j ||x_j|| (upper bound), for the certification margin
+};
+
+struct SearchWorkspace;
+
+// ---- kernels / launchers (one per .cu) ------------------------------------------------------------------
+// knn_filter_sm100.cu
+int filter_kp_for_k(int k);  // candidate-list capacity used for a given k, 0 = k too large for the filter
+int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int64_t nq, int metric, int kp,
+                      int n_splits, float* cand_score, int32_t* cand_id, float* cand_thr, int device,
+                      cudaStream_t stream);
+int filter_choose_splits(int64_t nq, int64_t n, int num_sms);
+
+// knn_exact.cu
+int launch_prep_queries(const void* q, int q_dtype, int64_t nq, int d, void* q_filt, int filt_dtype,
+                        int64_t filt_pitch, cudaStream_t stream);
+int launch_row_norms(const void* x, int dtype, int64_t n, int d, float* norm2, float* max_norm_dev,
+                     cudaStream_t stream);
+int launch_convert_pad(const void* x, int dtype, int64_t n, int d, void* out, int out_dtype, int64_t out_pitch,
+                       cudaStream_t stream);
+int launch_gather_rows(const void* x, int dtype, int d, const int64_t* ids, int64_t m, int64_t n, void* out,
+                       int* err_flag, cudaStream_t stream);
+int launch_finalize(const MatView& X, const void* q, int q_dtype, int64_t nq, int metric, int k, int kp,
+                    int n_splits, const float* cand_score, const int32_t* cand_id, const float* cand_thr,
+                    float rel_eps, const int64_t* id_map, int64_t id_offset, float* out_scores, int64_t* out_idx,
+                    int32_t* flags, cudaStream_t stream);
+int launch_dense_topk(const MatView& X, const void* q, int q_dtype, int64_t nq, const int32_t* q_sel,
+                      int64_t n_sel, int metric, int k, const int64_t* id_map, int64_t id_offset, float* dense_ws,
+                      int64_t dense_ws_rows, float* out_scores, int64_t* out_idx, cudaStream_t stream);
+int launch_merge_topk(const float* scores, const int64_t* idx, int g, int64_t nq, int k, int metric,
+                      float* out_scores, int64_t* out_idx, cudaStream_t stream);
+int dense_max_k();
+
+}  // namespace b2

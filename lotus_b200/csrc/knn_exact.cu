@@ -1,0 +1,788 @@
+// knn_exact.cu — the exact side of the search pipeline (everything that decides the reported result).
+//
+//   finalize_kernel   : per query (one warp): merge the per-split candidate lists of the tcgen05 filter with a
+//                       warp-shuffle bitonic network, re-score the KP survivors in the canonical fp64 order,
+//                       sort them, apply faiss's heap tie rule, and CERTIFY the result against everything the
+//                       filter discarded (rigorous error margin). Uncertified queries are flagged.
+//   dense_topk        : exact brute force for flagged queries and for k beyond the filter's capacity:
+//                       canonical scores for a batch of queries, block radix select, ordered tie collection.
+//   merge_topk_kernel : single-kernel k-way merge of per-shard (score, idx) lists after the NCCL all-gather.
+//   plus query preparation, row norms, padding/conversion and row gather (faiss_vs.py:38-41).
+//
+// Canonical score (bit-for-bit what oracle/faiss_flat.c `orc_dot_canonical` / `orc_l2_canonical` compute):
+// element i is accumulated by lane (i>>2)&31 in increasing i with fp64 fma; the 32 partials are combined by
+// a 16,8,4,2,1 xor-butterfly; the double is rounded once to fp32.
+#include "common.cuh"
+
+namespace b2 {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr uint64_t KEY_WORST = ~0ull;
+
+__device__ __forceinline__ double butterfly_sum(double v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+    return v;
+}
+
+__device__ __forceinline__ float elem_f32(const void* base, int dtype, size_t i) {
+    return dtype == B2_F32 ? reinterpret_cast<const float*>(base)[i]
+                           : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[i]);
+}
+
+// 4 consecutive elements of group g of a row (zero beyond d). `vec` = row start is 4-element aligned.
+__device__ __forceinline__ void load_group(const void* row, int dtype, int g, int d, bool vec, float (&o)[4]) {
+    const int i0 = g * 4;
+    if (vec) {
+        if (dtype == B2_F32) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(row) + g);
+            o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+        } else {
+            const uint2 t = __ldg(reinterpret_cast<const uint2*>(row) + g);
+            o[0] = __uint_as_float(t.x << 16);
+            o[1] = __uint_as_float(t.x & 0xffff0000u);
+            o[2] = __uint_as_float(t.y << 16);
+            o[3] = __uint_as_float(t.y & 0xffff0000u);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = (i0 + e < d) ? elem_f32(row, dtype, (size_t)(i0 + e)) : 0.f;
+    }
+}
+
+// canonical partial (this lane's share) of <q, x> or ||q - x||^2; q lives in shared memory as fp32
+template <bool IS_L2>
+__device__ __forceinline__ double canonical_partial(const float* q_s, const void* row, int dtype, int d, bool vec, int lane) {
+    double acc = 0.0;
+    const int ngroups = (d + 3) >> 2;
+    for (int g = lane; g < ngroups; g += 32) {
+        float x[4];
+        load_group(row, dtype, g, d, vec, x);
+        const float4 q4 = *reinterpret_cast<const float4*>(q_s + 4 * g);
+        const float qq[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (IS_L2) {
+                const double diff = (double)qq[e] - (double)x[e];
+                acc = fma(diff, diff, acc);
+            } else {
+                acc = fma((double)qq[e], (double)x[e], acc);
+            }
+        }
+    }
+    return acc;
+}
+
+// ---- warp-shuffle bitonic sort of 32*R u64 keys, element e = r*32 + lane, ascending ------------------------
+template <int R>
+__device__ __forceinline__ void warp_bitonic_sort(uint64_t (&key)[R], int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32 * R; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int jr = j >> 5;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int rp = r ^ jr;
+                    if (rp > r) {
+                        const bool up = (((r * 32) & k) == 0);  // k >= 64 here: independent of lane
+                        const uint64_t a = key[r], b = key[rp];
+                        const bool sw = (a > b) == up;
+                        key[r] = sw ? b : a;
+                        key[rp] = sw ? a : b;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int e = r * 32 + lane;
+                    const bool up = ((e & k) == 0);
+                    const uint64_t other = __shfl_xor_sync(FULL, key[r], j);
+                    const bool lower = ((lane & j) == 0);
+                    const bool keep_min = (lower == up);
+                    const uint64_t mn = key[r] < other ? key[r] : other;
+                    const uint64_t mx = key[r] < other ? other : key[r];
+                    key[r] = keep_min ? mn : mx;
+                }
+            }
+        }
+    }
+}
+
+// ---- small utility kernels -------------------------------------------------------------------------------------
+__global__ void prep_queries_kernel(const void* q, int q_dtype, int64_t nq, int d, void* out, int out_dtype, int64_t pitch) {
+    const int64_t total = nq * pitch;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / pitch;
+        const int c = (int)(t - r * pitch);
+        const float v = c < d ? elem_f32(q, q_dtype, (size_t)(r * d + c)) : 0.f;
+        if (out_dtype == B2_F32) reinterpret_cast<float*>(out)[t] = v;
+        else reinterpret_cast<__nv_bfloat16*>(out)[t] = __float2bfloat16_rn(v);
+    }
+}
+
+__global__ void row_norms_kernel(const void* x, int dtype, int64_t n, int d, float* norm2, float* max_norm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool vec = (d % 4) == 0;
+    const size_t esz = dtype == B2_F32 ? 4 : 2;
+    float local_max = 0.f;
+    for (int64_t j = warp; j < n; j += nwarps) {
+        const char* row = reinterpret_cast<const char*>(x) + (size_t)j * d * esz;
+        double acc = 0.0;
+        const int ngroups = (d + 3) >> 2;
+        for (int g = lane; g < ngroups; g += 32) {
+            float v[4];
+            load_group(row, dtype, g, d, vec, v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc = fma((double)v[e], (double)v[e], acc);
+        }
+        const double tot = butterfly_sum(acc);
+        if (lane == 0) norm2[j] = (float)tot;
+        local_max = fmaxf(local_max, (float)sqrt(tot) * (1.0f + 1e-6f));
+    }
+    if (lane == 0 && local_max > 0.f) atomicMax(reinterpret_cast<int*>(max_norm), __float_as_int(local_max));
+}
+
+__global__ void convert_pad_kernel(const void* x, int dtype, int64_t n, int d, void* out, int out_dtype, int64_t pitch) {
+    const int64_t total = n * pitch;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / pitch;
+        const int c = (int)(t - r * pitch);
+        const float v = c < d ? elem_f32(x, dtype, (size_t)(r * d + c)) : 0.f;
+        if (out_dtype == B2_F32) reinterpret_cast<float*>(out)[t] = v;
+        else reinterpret_cast<__nv_bfloat16*>(out)[t] = __float2bfloat16_rn(v);
+    }
+}
+
+// out[i,:] = x[ids[i],:] — one warp per row, 16-byte copies when the row size allows
+__global__ void gather_rows_kernel(const char* x, size_t row_bytes, const int64_t* ids, int64_t m, int64_t n, char* out,
+                                   int* err_flag) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < m; i += nwarps) {
+        const int64_t id = ids[i];
+        if (id < 0 || id >= n) {
+            if (lane == 0) atomicExch(err_flag, 1);
+            continue;
+        }
+        const char* src = x + (size_t)id * row_bytes;
+        char* dst = out + (size_t)i * row_bytes;
+        if ((row_bytes & 15) == 0) {
+            const int4* s4 = reinterpret_cast<const int4*>(src);
+            int4* d4 = reinterpret_cast<int4*>(dst);
+            for (size_t t = lane; t < row_bytes / 16; t += 32) d4[t] = __ldg(s4 + t);
+        } else {
+            const uint16_t* s2 = reinterpret_cast<const uint16_t*>(src);
+            uint16_t* d2 = reinterpret_cast<uint16_t*>(dst);
+            for (size_t t = lane; t < row_bytes / 2; t += 32) d2[t] = s2[t];
+        }
+    }
+}
+
+// ---- finalize ------------------------------------------------------------------------------------------------
+struct FinalizeParams {
+    const void* store;
+    const void* q;
+    const float* cand_score;
+    const int32_t* cand_id;
+    const float* cand_thr;
+    const int64_t* id_map;
+    float* out_scores;
+    int64_t* out_idx;
+    int32_t* flags;
+    int64_t nq;
+    int64_t id_offset;
+    int32_t d, dtype, q_dtype, metric, k, kp, n_splits;
+    float rel_eps, max_norm;
+};
+
+constexpr int FIN_WARPS = 4;
+
+template <int R>  // 32*R >= KP candidates survive the merge
+__global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(const FinalizeParams p) {
+    constexpr int NC = 32 * R;
+    extern __shared__ __align__(16) uint8_t fsm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d4 = ((p.d + 3) >> 2) << 2;
+    const size_t per_warp = (size_t)d4 * 4 + (size_t)NC * (4 + 4 + 8);
+    uint8_t* base = fsm + warp * per_warp;
+    uint64_t* s_keys = reinterpret_cast<uint64_t*>(base);         // [NC] sorted exact keys
+    float* q_s = reinterpret_cast<float*>(base + (size_t)NC * 8);  // [d4]
+    int32_t* s_id = reinterpret_cast<int32_t*>(q_s + d4);         // [NC]
+    float* s_ex = reinterpret_cast<float*>(s_id + NC);            // [NC]
+
+    const int64_t q = blockIdx.x * (int64_t)FIN_WARPS + warp;
+    if (q >= p.nq) return;
+    const bool is_l2 = p.metric == B2_METRIC_L2;
+    const bool vec = (p.d % 4) == 0;
+    const size_t esz = p.dtype == B2_F32 ? 4 : 2;
+
+    // 1. query -> smem (fp32, exact upcast for bf16) and its canonical squared norm
+    for (int i = lane; i < d4; i += 32) q_s[i] = i < p.d ? elem_f32(p.q, p.q_dtype, (size_t)q * p.d + i) : 0.f;
+    __syncwarp();
+    double qacc = 0.0;
+    for (int g = lane; g < (d4 >> 2); g += 32) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) qacc = fma((double)q_s[4 * g + e], (double)q_s[4 * g + e], qacc);
+    }
+    const double qn2 = butterfly_sum(qacc);
+
+    // 2. merge the per-split candidate lists by filter score (larger is better for both metrics)
+    uint64_t keys[2 * R];
+#pragma unroll
+    for (int r = 0; r < 2 * R; ++r) keys[r] = KEY_WORST;
+    float bound = -INFINITY;
+    for (int s = 0; s < p.n_splits; ++s) {
+        const size_t lbase = ((size_t)q * p.n_splits + s) * p.kp;
+        bound = fmaxf(bound, p.cand_thr[(size_t)q * p.n_splits + s]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int e = r * 32 + lane;
+            uint64_t kk = KEY_WORST;
+            if (e < p.kp) {
+                const int32_t id = p.cand_id[lbase + e];
+                if (id >= 0) kk = ((uint64_t)(~f32_ord(p.cand_score[lbase + e])) << 32) | (uint32_t)id;
+            }
+            keys[R + r] = kk;
+        }
+        if (s == 0) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                keys[r] = keys[R + r];
+                keys[R + r] = KEY_WORST;
+            }
+        } else {
+            warp_bitonic_sort<2 * R>(keys, lane);
+            // best discarded candidate (element NC of the sorted 2*NC) bounds everything dropped here
+            const uint64_t first_drop = __shfl_sync(FULL, keys[R], 0);
+            if (first_drop != KEY_WORST) bound = fmaxf(bound, f32_unord(~(uint32_t)(first_drop >> 32)));
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int e = r * 32 + lane;
+        s_id[e] = keys[r] == KEY_WORST ? -1 : (int32_t)(uint32_t)(keys[r] & 0xffffffffu);
+    }
+    __syncwarp();
+
+    // 3. canonical re-scoring of the NC survivors, four rows in flight
+    for (int c0 = 0; c0 < NC; c0 += 4) {
+        double part[4];
+        int32_t ids[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            ids[u] = s_id[c0 + u];
+            part[u] = 0.0;
+            if (ids[u] >= 0) {
+                const char* row = reinterpret_cast<const char*>(p.store) + (size_t)ids[u] * p.d * esz;
+                part[u] = is_l2 ? canonical_partial<true>(q_s, row, p.dtype, p.d, vec, lane)
+                                : canonical_partial<false>(q_s, row, p.dtype, p.d, vec, lane);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double tot = butterfly_sum(part[u]);
+            if (lane == 0) s_ex[c0 + u] = (float)tot;
+        }
+    }
+    __syncwarp();
+
+    // 4. exact keys: (score best first, then faiss's tie order: id ascending for L2, id descending for IP)
+    uint64_t ek[R];
+    int nvalid = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int e = r * 32 + lane;
+        const int32_t id = s_id[e];
+        if (id >= 0) {
+            const uint32_t tie = is_l2 ? (uint32_t)id : ~(uint32_t)id;
+            ek[r] = ((uint64_t)best_first_key(s_ex[e], p.metric) << 32) | tie;
+            nvalid++;
+        } else {
+            ek[r] = KEY_WORST;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) nvalid += __shfl_xor_sync(FULL, nvalid, off);
+    warp_bitonic_sort<R>(ek, lane);
+#pragma unroll
+    for (int r = 0; r < R; ++r) s_keys[r * 32 + lane] = ek[r];
+    __syncwarp();
+
+    // 5. faiss heap rule at rank k -> output positions
+    const int k = p.k;
+    const int nout = nvalid < k ? nvalid : k;
+    int c = nout, m = 0, t = 0, r_keep = 0;  // better-than-v count, ties at v, ties inside the first-k-by-id window
+    uint32_t vkey = 0;
+    if (nvalid > k) {
+        vkey = (uint32_t)(s_keys[k - 1] >> 32);
+        int cc = 0, mm = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t hk = (uint32_t)(ek[r] >> 32);
+            const bool valid = ek[r] != KEY_WORST;
+            cc += (valid && hk < vkey) ? 1 : 0;
+            mm += (valid && hk == vkey) ? 1 : 0;
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            cc += __shfl_xor_sync(FULL, cc, off);
+            mm += __shfl_xor_sync(FULL, mm, off);
+        }
+        c = cc;
+        m = mm;
+        r_keep = k - c;
+        t = m;
+        if (!is_l2 && m > r_keep) {
+            // ties inside the first k (by ascending id) elements of S = {score >= v}
+            int tt = 0;
+            for (int e = c + lane; e < c + m; e += 32) {
+                const uint32_t id_e = ~(uint32_t)(s_keys[e] & 0xffffffffu);
+                int rank = 1;
+                for (int f = 0; f < c + m; ++f) rank += (~(uint32_t)(s_keys[f] & 0xffffffffu) < id_e) ? 1 : 0;
+                tt += rank <= k ? 1 : 0;
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) tt += __shfl_xor_sync(FULL, tt, off);
+            t = tt;
+        }
+    }
+    // sorted ties sit at [c, c+m): L2 ascending id -> keep the first r; IP descending id (e_m .. e_1) -> keep e_t .. e_{t-r+1}
+    const int tie_src0 = (is_l2 || nvalid <= k) ? c : c + m - t;
+
+    // 6. certification against everything the filter discarded
+    bool certified = true;
+    if (bound > -INFINITY) {
+        if (nvalid < k) {
+            certified = false;  // cannot happen (lists only overflow when full); be safe
+        } else {
+            const double qn = sqrt(qn2);
+            const double v = (double)best_first_unkey((uint32_t)(s_keys[k - 1] >> 32), p.metric);
+            if (!is_l2) {
+                const double eps = (double)p.rel_eps * qn * (double)p.max_norm + 1e-30;
+                certified = ((double)bound + eps) < v;
+            } else {
+                const double mx = (double)p.max_norm;
+                const double eps_s = 2.0 * (double)p.rel_eps * qn * mx + 2.4e-7 * (mx * mx + 2.0 * qn * mx) + 1e-30;
+                // discarded rows have exact L2 >= qn2 - (bound + eps_s); allow for the fp32 rounding of v
+                certified = (qn2 - (double)bound - eps_s) > v * (1.0 + 2.4e-7) + 1e-30;
+            }
+        }
+    }
+
+    // 7. write
+    const float pad = is_l2 ? FLT_MAX : -FLT_MAX;
+    for (int o = lane; o < k; o += 32) {
+        float sc = pad;
+        int64_t oid = -1;
+        if (o < nout) {
+            const int src = o < c ? o : tie_src0 + (o - c);
+            const uint64_t kk = s_keys[src];
+            const uint32_t lo = (uint32_t)(kk & 0xffffffffu);
+            const int32_t id = (int32_t)(is_l2 ? lo : ~lo);
+            sc = best_first_unkey((uint32_t)(kk >> 32), p.metric);
+            oid = p.id_map ? p.id_map[id] : (int64_t)id + p.id_offset;
+        }
+        p.out_scores[(size_t)q * k + o] = sc;
+        p.out_idx[(size_t)q * k + o] = oid;
+    }
+    if (lane == 0) p.flags[q] = certified ? 0 : 1;
+}
+
+// ---- dense exact path -----------------------------------------------------------------------------------------
+// scores[s, j] = canonical score of selected query s against row j. One warp per row; the row's share stays
+// in registers/L1 while the warp walks the selected queries.
+__global__ void dense_scores_kernel(const void* store, int dtype, int64_t n, int d, const void* q, int q_dtype,
+                                    const int32_t* q_sel, int n_sel, int metric, float* out) {
+    extern __shared__ __align__(16) float dq[];  // [n_sel_chunk, d4] staged queries
+    const int lane = threadIdx.x & 31;
+    const int d4 = ((d + 3) >> 2) << 2;
+    const bool vec = (d % 4) == 0;
+    const size_t esz = dtype == B2_F32 ? 4 : 2;
+    const bool is_l2 = metric == B2_METRIC_L2;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    constexpr int QCHUNK = 8;
+    for (int s0 = 0; s0 < n_sel; s0 += QCHUNK) {
+        const int sc = min(QCHUNK, n_sel - s0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < sc * d4; t += blockDim.x) {
+            const int s = t / d4, i = t - s * d4;
+            const int64_t qi = q_sel ? q_sel[s0 + s] : (s0 + s);
+            dq[t] = i < d ? elem_f32(q, q_dtype, (size_t)qi * d + i) : 0.f;
+        }
+        __syncthreads();
+        for (int64_t j = warp; j < n; j += nwarps) {
+            const char* row = reinterpret_cast<const char*>(store) + (size_t)j * d * esz;
+            for (int s = 0; s < sc; ++s) {
+                const double part = is_l2 ? canonical_partial<true>(dq + s * d4, row, dtype, d, vec, lane)
+                                          : canonical_partial<false>(dq + s * d4, row, dtype, d, vec, lane);
+                const double tot = butterfly_sum(part);
+                if (lane == 0) out[(size_t)(s0 + s) * n + j] = (float)tot;
+            }
+        }
+    }
+}
+
+constexpr int SEL_THREADS = 512;
+constexpr int SEL_MAX_K = 2048;
+
+// ordered exclusive count of `flag` across the block (thread order), plus the block total
+__device__ __forceinline__ int block_excl_count(bool flag, int* s_warp, int& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned b = __ballot_sync(FULL, flag);
+    const int in_warp = __popc(b & ((1u << lane) - 1));
+    __syncthreads();
+    if (lane == 0) s_warp[warp] = __popc(b);
+    __syncthreads();
+    int before = 0, tot = 0;
+    for (int w = 0; w < SEL_THREADS / 32; ++w) {
+        const int cw = s_warp[w];
+        before += w < warp ? cw : 0;
+        tot += cw;
+    }
+    total = tot;
+    return before + in_warp;
+}
+
+// One CTA per selected query: exact top-k of scores[s, 0..n) under faiss's heap rule.
+__global__ void __launch_bounds__(SEL_THREADS)
+dense_select_kernel(const float* scores, int64_t n, const int32_t* q_sel, int metric, int k, const int64_t* id_map,
+                    int64_t id_offset, float* out_scores, int64_t* out_idx) {
+    __shared__ int hist[256];
+    __shared__ int s_warp[SEL_THREADS / 32];
+    __shared__ uint32_t s_prefix, s_mask;
+    __shared__ int s_kk, s_nbetter, s_nties;
+    __shared__ uint64_t s_out[SEL_MAX_K];      // collected (key<<32 | tie-order id), later sorted
+    __shared__ uint32_t s_ties[SEL_MAX_K];     // ids of the ties inside the first-k-by-id window, ascending
+    const int s = blockIdx.x;
+    const int64_t qo = q_sel ? q_sel[s] : s;
+    const float* row = scores + (size_t)s * n;
+    const bool is_l2 = metric == B2_METRIC_L2;
+    const int tid = threadIdx.x;
+    const int keff = (int)(n < k ? n : k);
+
+    uint32_t vkey = 0xffffffffu;
+    int r_keep = 0;
+    if (n > k) {
+        // radix select: the k-th smallest best-first key
+        if (tid == 0) { s_prefix = 0; s_mask = 0; s_kk = k; }
+        __syncthreads();
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
+            __syncthreads();
+            const uint32_t prefix = s_prefix, mask = s_mask;
+            for (int64_t j = tid; j < n; j += SEL_THREADS) {
+                const uint32_t key = best_first_key(row[j], metric);
+                if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int kk = s_kk, cum = 0, b = 0;
+                for (b = 0; b < 256; ++b) {
+                    if (cum + hist[b] >= kk) break;
+                    cum += hist[b];
+                }
+                s_kk = kk - cum;
+                s_prefix = prefix | ((uint32_t)b << shift);
+                s_mask = mask | (0xffu << shift);
+            }
+            __syncthreads();
+        }
+        vkey = s_prefix;
+        r_keep = s_kk;  // ties at vkey that belong to the top k
+    }
+    if (tid == 0) { s_nbetter = 0; s_nties = 0; }
+    __syncthreads();
+
+    // collect everything strictly better than v (unordered), and the ties inside the first k of S by id (ordered)
+    int running_s = 0;
+    for (int64_t base = 0; base < n; base += SEL_THREADS) {
+        const int64_t j = base + tid;
+        uint32_t key = 0xffffffffu;
+        bool in_s = false, is_tie = false, better = false;
+        if (j < n) {
+            key = best_first_key(row[j], metric);
+            if (n > k) {
+                better = key < vkey;
+                is_tie = key == vkey;
+                in_s = better || is_tie;
+            } else {
+                better = true;
+            }
+        }
+        if (better) {
+            const int slot = atomicAdd(&s_nbetter, 1);
+            const uint32_t tie = is_l2 ? (uint32_t)j : ~(uint32_t)j;
+            if (slot < SEL_MAX_K) s_out[slot] = ((uint64_t)key << 32) | tie;
+        }
+        if (n > k && running_s < k) {  // running_s is block-uniform
+            if (__syncthreads_or(in_s)) {
+                int tot_s = 0;
+                const int pos = running_s + block_excl_count(in_s, s_warp, tot_s);
+                const bool tie_in_window = is_tie && pos < k;
+                int tot_t = 0;
+                const int tpos = block_excl_count(tie_in_window, s_warp, tot_t);
+                const int tbase = s_nties;
+                if (tie_in_window && tbase + tpos < SEL_MAX_K) s_ties[tbase + tpos] = (uint32_t)j;
+                __syncthreads();
+                if (tid == 0) s_nties = tbase + tot_t;
+                running_s += tot_s;
+                __syncthreads();
+            }
+        }
+    }
+    __syncthreads();
+    const int c = s_nbetter;
+    if (n > k) {
+        const int t = s_nties;
+        // L2: first r ties (ascending id). IP: the last r of the t window ties (e_{t-r+1} .. e_t).
+        const int first = is_l2 ? 0 : t - r_keep;
+        for (int i = tid; i < r_keep; i += SEL_THREADS) {
+            const uint32_t id = s_ties[first + i];
+            s_out[c + i] = ((uint64_t)vkey << 32) | (is_l2 ? id : ~id);
+        }
+    }
+    // sort the keff collected entries (bitonic in shared memory, padded with worst keys)
+    int npow = 1;
+    while (npow < keff) npow <<= 1;
+    __syncthreads();
+    for (int i = keff + tid; i < npow; i += SEL_THREADS) s_out[i] = KEY_WORST;
+    __syncthreads();
+    for (int kk = 2; kk <= npow; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < npow; i += SEL_THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const bool up = (i & kk) == 0;
+                    const uint64_t a = s_out[i], b = s_out[ixj];
+                    if ((a > b) == up) { s_out[i] = b; s_out[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const float pad = is_l2 ? FLT_MAX : -FLT_MAX;
+    for (int o = tid; o < k; o += SEL_THREADS) {
+        float sc = pad;
+        int64_t oid = -1;
+        if (o < keff) {
+            const uint64_t kk2 = s_out[o];
+            const uint32_t lo = (uint32_t)(kk2 & 0xffffffffu);
+            const int64_t id = (int64_t)(is_l2 ? lo : ~lo);
+            sc = best_first_unkey((uint32_t)(kk2 >> 32), metric);
+            oid = id_map ? id_map[id] : id + id_offset;
+        }
+        out_scores[(size_t)qo * k + o] = sc;
+        out_idx[(size_t)qo * k + o] = oid;
+    }
+}
+
+// ---- k-way merge of per-shard lists -----------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(128) merge_topk_kernel(const float* scores, const int64_t* idx, int g, int64_t nq, int k,
+                                                         int metric, float* out_scores, int64_t* out_idx) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t q = blockIdx.x * 4LL + warp;
+    if (q >= nq) return;
+    const bool is_l2 = metric == B2_METRIC_L2;
+    const int total = g * k;
+    uint64_t keys[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int e = r * 32 + lane;
+        uint64_t kk = KEY_WORST;
+        if (e < total) {
+            const int gi = e / k, pi = e - gi * k;
+            const size_t off = ((size_t)gi * nq + q) * k + pi;
+            if (idx[off] >= 0) {
+                // equal scores: shard lists are already in faiss tie order; lower shards hold lower ids
+                const uint32_t tie = is_l2 ? (uint32_t)e : (uint32_t)((g - 1 - gi) * k + pi);
+                kk = ((uint64_t)best_first_key(scores[off], metric) << 32) | tie;
+            }
+        }
+        keys[r] = kk;
+    }
+    warp_bitonic_sort<R>(keys, lane);
+    const float pad = is_l2 ? FLT_MAX : -FLT_MAX;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int o = r * 32 + lane;
+        if (o < k) {
+            float sc = pad;
+            int64_t oid = -1;
+            if (keys[r] != KEY_WORST) {
+                const uint32_t tie = (uint32_t)(keys[r] & 0xffffffffu);
+                int gi, pi;
+                if (is_l2) { gi = tie / k; pi = tie - gi * k; }
+                else { const int gr = tie / k; pi = tie - gr * k; gi = g - 1 - gr; }
+                const size_t off = ((size_t)gi * nq + q) * k + pi;
+                sc = scores[off];
+                oid = idx[off];
+            }
+            out_scores[(size_t)q * k + o] = sc;
+            out_idx[(size_t)q * k + o] = oid;
+        }
+    }
+}
+
+int grid_for(int64_t work_items, int threads, int cap = 148 * 16) {
+    int64_t g = ceil_div(work_items, threads);
+    if (g < 1) g = 1;
+    return (int)std::min<int64_t>(g, cap);
+}
+
+}  // namespace
+
+int dense_max_k() { return SEL_MAX_K; }
+
+int launch_prep_queries(const void* q, int q_dtype, int64_t nq, int d, void* q_filt, int filt_dtype,
+                        int64_t filt_pitch, cudaStream_t stream) {
+    if (nq <= 0) return B2_OK;
+    prep_queries_kernel<<<grid_for(nq * filt_pitch, 256), 256, 0, stream>>>(q, q_dtype, nq, d, q_filt, filt_dtype, filt_pitch);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+int launch_row_norms(const void* x, int dtype, int64_t n, int d, float* norm2, float* max_norm_dev, cudaStream_t stream) {
+    B2_CUDA(cudaMemsetAsync(max_norm_dev, 0, sizeof(float), stream));
+    if (n <= 0) return B2_OK;
+    row_norms_kernel<<<grid_for(n * 32, 256), 256, 0, stream>>>(x, dtype, n, d, norm2, max_norm_dev);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+int launch_convert_pad(const void* x, int dtype, int64_t n, int d, void* out, int out_dtype, int64_t out_pitch,
+                       cudaStream_t stream) {
+    if (n <= 0) return B2_OK;
+    convert_pad_kernel<<<grid_for(n * out_pitch, 256), 256, 0, stream>>>(x, dtype, n, d, out, out_dtype, out_pitch);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+int launch_gather_rows(const void* x, int dtype, int d, const int64_t* ids, int64_t m, int64_t n, void* out,
+                       int* err_flag, cudaStream_t stream) {
+    if (m <= 0) return B2_OK;
+    const size_t row_bytes = (size_t)d * (dtype == B2_F32 ? 4 : 2);
+    gather_rows_kernel<<<grid_for(m * 32, 256), 256, 0, stream>>>(reinterpret_cast<const char*>(x), row_bytes, ids, m, n,
+                                                                  reinterpret_cast<char*>(out), err_flag);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+template <int R>
+static int launch_finalize_r(const FinalizeParams& p, cudaStream_t stream) {
+    const int d4 = ((p.d + 3) >> 2) << 2;
+    const size_t smem = (size_t)FIN_WARPS * ((size_t)d4 * 4 + (size_t)(32 * R) * 16);
+    auto kern = finalize_kernel<R>;
+    if (smem > 48 * 1024) {
+        if (smem > 200 * 1024) {
+            set_error("embedding dimension %d too large for the finalize kernel", p.d);
+            return B2_ERANGE;
+        }
+        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    kern<<<(unsigned)ceil_div(p.nq, FIN_WARPS), FIN_WARPS * 32, smem, stream>>>(p);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+int launch_finalize(const MatView& X, const void* q, int q_dtype, int64_t nq, int metric, int k, int kp,
+                    int n_splits, const float* cand_score, const int32_t* cand_id, const float* cand_thr,
+                    float rel_eps, const int64_t* id_map, int64_t id_offset, float* out_scores, int64_t* out_idx,
+                    int32_t* flags, cudaStream_t stream) {
+    if (nq <= 0) return B2_OK;
+    FinalizeParams p;
+    p.store = X.store;
+    p.q = q;
+    p.cand_score = cand_score;
+    p.cand_id = cand_id;
+    p.cand_thr = cand_thr;
+    p.id_map = id_map;
+    p.out_scores = out_scores;
+    p.out_idx = out_idx;
+    p.flags = flags;
+    p.nq = nq;
+    p.id_offset = id_offset;
+    p.d = X.d;
+    p.dtype = X.dtype;
+    p.q_dtype = q_dtype;
+    p.metric = metric;
+    p.k = k;
+    p.kp = kp;
+    p.n_splits = n_splits;
+    p.rel_eps = rel_eps;
+    p.max_norm = X.max_norm;
+    g_stats[ST_RESCORED] += nq * (int64_t)kp;
+    if (kp <= 32) return launch_finalize_r<1>(p, stream);
+    if (kp <= 64) return launch_finalize_r<2>(p, stream);
+    if (kp <= 128) return launch_finalize_r<4>(p, stream);
+    set_error("internal: finalize capacity %d", kp);
+    return B2_EINVAL;
+}
+
+int launch_dense_topk(const MatView& X, const void* q, int q_dtype, int64_t nq, const int32_t* q_sel, int64_t n_sel,
+                      int metric, int k, const int64_t* id_map, int64_t id_offset, float* dense_ws,
+                      int64_t dense_ws_rows, float* out_scores, int64_t* out_idx, cudaStream_t stream) {
+    (void)nq;
+    if (n_sel <= 0) return B2_OK;
+    if (k > SEL_MAX_K) {
+        set_error("k=%d exceeds the dense path's limit %d", k, SEL_MAX_K);
+        return B2_ERANGE;
+    }
+    const int d4 = ((X.d + 3) >> 2) << 2;
+    const size_t smem = (size_t)8 * d4 * 4;
+    if (smem > 48 * 1024) {
+        if (smem > 200 * 1024) {
+            set_error("embedding dimension %d too large for the dense path", X.d);
+            return B2_ERANGE;
+        }
+        B2_CUDA(cudaFuncSetAttribute(dense_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    for (int64_t s0 = 0; s0 < n_sel; s0 += dense_ws_rows) {
+        const int sc = (int)std::min<int64_t>(dense_ws_rows, n_sel - s0);
+        const int32_t* sel = q_sel ? q_sel + s0 : nullptr;
+        // without a selection list the batch is the contiguous query range [s0, s0+sc)
+        const void* qb = q_sel ? q : reinterpret_cast<const char*>(q) + (size_t)s0 * X.d * (q_dtype == B2_F32 ? 4 : 2);
+        if (X.n > 0) {
+            dense_scores_kernel<<<grid_for(X.n * 32, 256, 148 * 8), 256, smem, stream>>>(X.store, X.dtype, X.n, X.d, qb, q_dtype,
+                                                                                       sel, sc, metric, dense_ws);
+            B2_LAUNCH_CHECK();
+        }
+        float* os = q_sel ? out_scores : out_scores + (size_t)s0 * k;
+        int64_t* oi = q_sel ? out_idx : out_idx + (size_t)s0 * k;
+        dense_select_kernel<<<sc, SEL_THREADS, 0, stream>>>(dense_ws, X.n, sel, metric, k, id_map, id_offset, os, oi);
+        B2_LAUNCH_CHECK();
+    }
+    return B2_OK;
+}
+
+int launch_merge_topk(const float* scores, const int64_t* idx, int g, int64_t nq, int k, int metric, float* out_scores,
+                      int64_t* out_idx, cudaStream_t stream) {
+    if (nq <= 0) return B2_OK;
+    const int total = g * k;
+    const unsigned grid = (unsigned)ceil_div(nq, 4);
+#define B2_MERGE_CASE(RR)                                                                                        \
+    if (total <= 32 * RR) {                                                                                      \
+        merge_topk_kernel<RR><<<grid, 128, 0, stream>>>(scores, idx, g, nq, k, metric, out_scores, out_idx);     \
+        B2_LAUNCH_CHECK();                                                                                       \
+        return B2_OK;                                                                                            \
+    }
+    B2_MERGE_CASE(1)
+    B2_MERGE_CASE(2)
+    B2_MERGE_CASE(4)
+    B2_MERGE_CASE(8)
+    B2_MERGE_CASE(16)
+    B2_MERGE_CASE(32)
+#undef B2_MERGE_CASE
+    set_error("merge of %d lists x k=%d exceeds 1024 candidates per query", g, k);
+    return B2_ERANGE;
+}
+
+}  // namespace b2

@@ -1,0 +1,578 @@
+// knn_filter_sm100.cu — the dominant kernel: fused Q.K^T (tcgen05 tensor cores, TMEM accumulators,
+// TMA-staged operand tiles) + per-query streaming top-KP selection in the epilogue.
+//
+// Replaces the arithmetic of faiss `Index.search` as called from lotus/vector_store/faiss_vs.py:67,75
+// (knn_inner_product / knn_L2sqr: blocked sgemm + heap). The N x Q score matrix is never written to HBM.
+//
+// Role of this kernel in the exact pipeline: it is a FILTER. It computes scores with
+// bf16 (or TF32) tensor-core products and fp32 accumulation and keeps, per query and per corpus split,
+// the KP > k best candidates plus the value `thr` below which everything was discarded. knn_exact.cu then
+// re-scores the candidates in the canonical fp64 order and certifies, with a rigorous error margin, that
+// nothing discarded could belong to the true top-k; uncertified queries take the dense exact path.
+//
+// Kernel shape (cta_group::1):
+//   CTA tile 128 queries x 256 corpus rows, K-block = one 128-byte swizzle row (64 bf16 / 32 tf32),
+//   UMMA 128x256x16 (bf16) or 128x256x8 (tf32), fp32 accumulators double-buffered in TMEM (2 x 256 cols).
+//   warp 0: TMA producer (one elected lane)      warp 1: MMA issuer (one elected lane)
+//   warp 2: TMEM allocator                       warps 4-7: epilogue, thread r <-> query row r <-> TMEM lane r
+//   smem ring of NSTAGES x (A 16 KB + B 32 KB), mbarrier full/empty pairs; tmem_full/tmem_empty pairs.
+//   Persistent: grid = #SMs, work item = (query tile, corpus split), query tile fastest so that co-resident
+//   CTAs stream the same corpus tiles and hit them in L2.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace b2 {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int STAGE_A_BYTES = BLOCK_M * 128;
+constexpr int STAGE_B_BYTES = BLOCK_N * 128;
+constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_LIMIT = 232448;  // 227 KB
+
+__host__ __device__ constexpr int list_bytes(int kp) { return kp * BLOCK_M * 8; }
+__host__ __device__ constexpr int misc_bytes() { return 2 * BLOCK_N * 4 /*xnorm*/ + 256 /*barriers*/; }
+__host__ __device__ constexpr int num_stages(int kp) {
+    int s = (SMEM_LIMIT - list_bytes(kp) - misc_bytes()) / STAGE_BYTES;
+    return s > 6 ? 6 : s;
+}
+__host__ __device__ constexpr int smem_bytes(int kp) { return num_stages(kp) * STAGE_BYTES + list_bytes(kp) + misc_bytes(); }
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug must trap (sticky error the host reports) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    uint32_t spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (++spins > (1u << 26)) {  // each failed try_wait already blocks for a HW time slice; this is seconds
+            printf("b2 knn_filter: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (TF32) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives lane (base+t), columns c..c+31
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor: K-major operand tile, rows of 128 bytes, SWIZZLE_128B (the layout a
+// TMA box {128 B, rows} with CU_TENSOR_MAP_SWIZZLE_128B lands in). 8-row groups are 1024 B apart (SBO).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t desc = 0;
+    desc |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
+    desc |= (uint64_t)1 << 16;                        // leading byte offset (ignored for swizzled K-major)
+    desc |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset, bits [32,46)
+    desc |= (uint64_t)1 << 46;                        // descriptor version 1 (sm_100)
+    desc |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
+    return desc;
+}
+// UMMA instruction descriptor: D fp32, A/B bf16 (1) or tf32 (2), both K-major, M = 128, N = 256.
+template <bool TF32>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+    const uint32_t fmt = TF32 ? 2u : 1u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+struct FilterParams {
+    const float* xnorm;  // [n], L2 only
+    float* cand_score;   // [nq, n_splits, KP]
+    int32_t* cand_id;    // [nq, n_splits, KP]
+    float* cand_thr;     // [nq, n_splits]
+    int32_t nq;
+    int32_t n;
+    int32_t num_kb;        // K-blocks per tile = ceil(d / elements per 128 B)
+    int32_t n_mtiles;      // ceil(nq / 128)
+    int32_t n_splits;
+    int32_t tiles_per_split;  // corpus tiles (of 256 rows) per split
+    int32_t n_ntiles;         // ceil(n / 256)
+};
+
+// Replace-min insertion into the thread's candidate list (column `row` of sc/id, stride BLOCK_M).
+// Returns the new threshold (min of the list; -inf while a slot is free) and its position.
+template <int KP>
+__device__ __noinline__ float2 list_insert(float* sc, int32_t* id, float s, int32_t idx, int minpos) {
+    sc[minpos * BLOCK_M] = s;
+    id[minpos * BLOCK_M] = idx;
+    float m = sc[0];
+    int mp = 0;
+#pragma unroll 8
+    for (int p = 1; p < KP; ++p) {
+        float v = sc[p * BLOCK_M];
+        if (v < m) {
+            m = v;
+            mp = p;
+        }
+    }
+    return make_float2(m, __int_as_float(mp));
+}
+
+template <int KP, bool IS_L2, bool TF32>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
+                  const FilterParams p) {
+    constexpr int NSTAGES = num_stages(KP);
+    static_assert(NSTAGES >= 2, "not enough shared memory for the operand ring");
+    constexpr int KB_ELEMS = TF32 ? 32 : 64;  // elements per 128-byte K-block row
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* stage_base = smem;
+    float* list_sc = reinterpret_cast<float*>(smem + NSTAGES * STAGE_BYTES);
+    int32_t* list_id = reinterpret_cast<int32_t*>(list_sc + KP * BLOCK_M);
+    float* s_xn = reinterpret_cast<float*>(list_id + KP * BLOCK_M);  // [2][BLOCK_N]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_xn + 2 * BLOCK_N);
+    uint64_t* full_bar = bars;                 // [NSTAGES]
+    uint64_t* empty_bar = bars + NSTAGES;      // [NSTAGES]
+    uint64_t* tmem_full = bars + 2 * NSTAGES;  // [2]
+    uint64_t* tmem_empty = tmem_full + 2;      // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if ((smem_u32(smem) & 1023u) != 0) {
+        if (threadIdx.x == 0) printf("b2 knn_filter: dynamic smem base not 1024-aligned\n");
+        __trap();
+    }
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_x);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < NSTAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int n_items = p.n_mtiles * p.n_splits;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int m_tile = item % p.n_mtiles;
+                const int split = item / p.n_mtiles;
+                const int t0 = split * p.tiles_per_split;
+                const int t1 = min(t0 + p.tiles_per_split, p.n_ntiles);
+                for (int t = t0; t < t1; ++t) {
+                    for (int kb = 0; kb < p.num_kb; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = stage_base + stage * STAGE_BYTES;
+                        uint8_t* sb = sa + STAGE_A_BYTES;
+                        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                        tma_load_2d(sa, &tmap_q, &full_bar[stage], kb * KB_ELEMS, m_tile * BLOCK_M);
+                        tma_load_2d(sb, &tmap_x, &full_bar[stage], kb * KB_ELEMS, t * BLOCK_N);
+                        if (++stage == NSTAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc<TF32>();
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int split = item / p.n_mtiles;
+                const int t0 = split * p.tiles_per_split;
+                const int t1 = min(t0 + p.tiles_per_split, p.n_ntiles);
+                for (int t = t0; t < t1; ++t) {
+                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                    for (int kb = 0; kb < p.num_kb; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(stage_base + stage * STAGE_BYTES);
+                        const uint64_t adesc = make_sw128_desc(sa);
+                        const uint64_t bdesc = make_sw128_desc(sa + STAGE_A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            // +32 bytes per UMMA_K step inside the 128-byte swizzle row (start address is in 16 B units)
+                            tc_mma<TF32>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                         (kb | k) != 0 ? 1u : 0u);
+                        }
+                        tc_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+                        if (++stage == NSTAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+                    if (++acc == 2) {
+                        acc = 0;
+                        acc_phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===================== epilogue: streaming top-KP per query row =====================
+        const int quad = warp - EPI_WARP0;   // == warp % 4: the TMEM lane quarter this warp may read
+        const int row = quad * 32 + lane;    // query row inside the tile == TMEM lane
+        const int epi_tid = threadIdx.x - EPI_WARP0 * 32;
+        float* my_sc = list_sc + row;
+        int32_t* my_id = list_id + row;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int m_tile = item % p.n_mtiles;
+            const int split = item / p.n_mtiles;
+            const int t0 = split * p.tiles_per_split;
+            const int t1 = min(t0 + p.tiles_per_split, p.n_ntiles);
+#pragma unroll 4
+            for (int i = 0; i < KP; ++i) {
+                my_sc[i * BLOCK_M] = -INFINITY;
+                my_id[i * BLOCK_M] = -1;
+            }
+            float thr = -INFINITY;
+            int minpos = 0;
+            for (int t = t0; t < t1; ++t) {
+                const int col0 = t * BLOCK_N;
+                if constexpr (IS_L2) {
+                    // stage this tile's squared norms; the 4 epilogue warps sync on named barrier 1
+                    float* xn = s_xn + acc * BLOCK_N;
+                    for (int c = epi_tid; c < BLOCK_N; c += 128) {
+                        const int g = col0 + c;
+                        xn[c] = g < p.n ? __ldg(p.xnorm + g) : 0.f;
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+                const int ncols = min(BLOCK_N, p.n - col0);
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    float v[32];
+                    tmem_ld32(taddr + c * 32, v);
+                    tmem_ld_wait();
+                    if (c == BLOCK_N / 32 - 1) {
+                        // whole accumulator stage now in registers: hand TMEM back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    }
+                    if constexpr (IS_L2) {
+                        const float4* xn4 = reinterpret_cast<const float4*>(s_xn + acc * BLOCK_N + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 x4 = xn4[j];  // warp-uniform address: broadcast
+                            v[4 * j + 0] = fmaf(2.f, v[4 * j + 0], -x4.x);
+                            v[4 * j + 1] = fmaf(2.f, v[4 * j + 1], -x4.y);
+                            v[4 * j + 2] = fmaf(2.f, v[4 * j + 2], -x4.z);
+                            v[4 * j + 3] = fmaf(2.f, v[4 * j + 3], -x4.w);
+                        }
+                    }
+                    const int valid = ncols - c * 32;  // warp-uniform
+                    if (valid <= 0) continue;
+                    if (valid < 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j >= valid) v[j] = -INFINITY;
+                    }
+                    float mx = v[0];
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+                    if (mx > thr) {
+                        const int idx0 = col0 + c * 32;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (v[j] > thr) {
+                                const float2 r = list_insert<KP>(my_sc, my_id, v[j], idx0 + j, minpos);
+                                thr = r.x;
+                                minpos = __float_as_int(r.y);
+                            }
+                        }
+                    }
+                }
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+            // write this (query, split) candidate list
+            const int q = m_tile * BLOCK_M + row;
+            if (q < p.nq) {
+                const size_t base = ((size_t)q * p.n_splits + split) * KP;
+                float4* osc = reinterpret_cast<float4*>(p.cand_score + base);
+                int4* oid = reinterpret_cast<int4*>(p.cand_id + base);
+#pragma unroll 4
+                for (int i = 0; i < KP / 4; ++i) {
+                    osc[i] = make_float4(my_sc[(4 * i + 0) * BLOCK_M], my_sc[(4 * i + 1) * BLOCK_M],
+                                         my_sc[(4 * i + 2) * BLOCK_M], my_sc[(4 * i + 3) * BLOCK_M]);
+                    oid[i] = make_int4(my_id[(4 * i + 0) * BLOCK_M], my_id[(4 * i + 1) * BLOCK_M],
+                                       my_id[(4 * i + 2) * BLOCK_M], my_id[(4 * i + 3) * BLOCK_M]);
+                }
+                p.cand_thr[(size_t)q * p.n_splits + split] = thr;  // -inf unless the list overflowed
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver (%s)", cudaGetErrorString(e));
+        return nullptr;
+    }
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+    return fn;
+}
+
+// 2-D row-major matrix [rows, cols] with `pitch` elements per row; box = {128 bytes of K, box_rows rows}
+int make_tmap(CUtensorMap* map, const void* base, bool tf32, int64_t rows, int64_t cols, int64_t pitch, int box_rows) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return B2_ECUDA;
+    const int esz = tf32 ? 4 : 2;
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)pitch * esz};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (gstride[0] & 15) != 0) {
+        set_error("TMA operand not 16-byte aligned (base %p, pitch %lld B)", base, (long long)gstride[0]);
+        return B2_EINVAL;
+    }
+    CUresult r = enc(map, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                     const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %lld cols %lld pitch %lld)", (int)r,
+                  (long long)rows, (long long)cols, (long long)pitch);
+        return B2_ECUDA;
+    }
+    return B2_OK;
+}
+
+template <int KP, bool IS_L2, bool TF32>
+int launch_variant(const CUtensorMap& tq, const CUtensorMap& tx, const FilterParams& p, int grid, cudaStream_t stream) {
+    auto kern = knn_filter_kernel<KP, IS_L2, TF32>;
+    constexpr int smem = smem_bytes(KP);
+    static bool attr_set = false;
+    if (!attr_set) {
+        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    kern<<<grid, NUM_THREADS, smem, stream>>>(tq, tx, p);
+    B2_LAUNCH_CHECK();
+    g_stats[ST_FILTER_LAUNCHES]++;
+    return B2_OK;
+}
+
+template <int KP>
+int launch_kp(bool is_l2, bool tf32, const CUtensorMap& tq, const CUtensorMap& tx, const FilterParams& p, int grid,
+              cudaStream_t stream) {
+    if (is_l2) {
+        return tf32 ? launch_variant<KP, true, true>(tq, tx, p, grid, stream)
+                    : launch_variant<KP, true, false>(tq, tx, p, grid, stream);
+    }
+    return tf32 ? launch_variant<KP, false, true>(tq, tx, p, grid, stream)
+                : launch_variant<KP, false, false>(tq, tx, p, grid, stream);
+}
+
+int sm_count(int device) {
+    static int cached[64] = {0};
+    if (device >= 0 && device < 64 && cached[device]) return cached[device];
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+    if (device >= 0 && device < 64) cached[device] = n;
+    return n;
+}
+
+}  // namespace
+
+int filter_kp_for_k(int k) {
+    if (k <= 6) return 16;
+    if (k <= 16) return 32;
+    if (k <= 40) return 64;
+    if (k <= 96) return 128;
+    return 0;
+}
+
+// Number of corpus splits: enough work items to fill the machine, and few idle SMs in the last wave.
+int filter_choose_splits(int64_t nq, int64_t n, int num_sms) {
+    const int64_t n_mtiles = ceil_div(nq, BLOCK_M);
+    const int64_t n_ntiles = ceil_div(n, BLOCK_N);
+    int best = 1;
+    double best_eff = -1.0;
+    for (int s = 1; s <= 256 && s <= n_ntiles; ++s) {
+        const int64_t tps = ceil_div(n_ntiles, s);
+        const int64_t s_eff = ceil_div(n_ntiles, tps);  // splits that actually receive tiles
+        if (s_eff != s) continue;
+        const int64_t items = n_mtiles * s;
+        const int64_t waves = ceil_div(items, num_sms);
+        double eff = (double)items / (double)(waves * num_sms);
+        // each split restarts its candidate lists and adds finalize work: prefer fewer, longer splits
+        if (tps < 4 && s > 1) eff -= 0.25;
+        eff -= 0.002 * s;
+        if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best = s;
+        }
+        if (items >= 8 * (int64_t)num_sms && eff > 0.93) break;
+    }
+    return best;
+}
+
+int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int64_t nq, int metric, int kp,
+                      int n_splits, float* cand_score, int32_t* cand_id, float* cand_thr, int device,
+                      cudaStream_t stream) {
+    if (nq <= 0 || X.n <= 0) return B2_OK;
+    if (X.n > 0x7fffff00LL || nq > 0x7fffff00LL) {
+        set_error("matrix too large for 32-bit row ids (n=%lld nq=%lld)", (long long)X.n, (long long)nq);
+        return B2_ERANGE;
+    }
+    const bool tf32 = X.dtype == B2_F32;
+    const int kb_elems = tf32 ? 32 : 64;
+    CUtensorMap tq, tx;
+    B2_TRY(make_tmap(&tq, q_filt, tf32, nq, X.d, q_pitch, BLOCK_M));
+    B2_TRY(make_tmap(&tx, X.filt, tf32, X.n, X.d, X.filt_pitch, BLOCK_N));
+    FilterParams p;
+    p.xnorm = X.norm2;
+    p.cand_score = cand_score;
+    p.cand_id = cand_id;
+    p.cand_thr = cand_thr;
+    p.nq = (int32_t)nq;
+    p.n = (int32_t)X.n;
+    p.num_kb = (int32_t)ceil_div(X.d, kb_elems);
+    p.n_mtiles = (int32_t)ceil_div(nq, BLOCK_M);
+    p.n_ntiles = (int32_t)ceil_div(X.n, BLOCK_N);
+    p.tiles_per_split = (int32_t)ceil_div(p.n_ntiles, n_splits);
+    p.n_splits = n_splits;
+    if ((int64_t)p.tiles_per_split * (n_splits - 1) >= p.n_ntiles) {
+        set_error("internal: empty corpus split (tiles %d, splits %d)", p.n_ntiles, n_splits);
+        return B2_EINVAL;
+    }
+    const int64_t items = (int64_t)p.n_mtiles * n_splits;
+    const int grid = (int)std::min<int64_t>(items, sm_count(device));
+    const bool is_l2 = metric == B2_METRIC_L2;
+    if (is_l2 && !X.norm2) {
+        set_error("internal: L2 filter without row norms");
+        return B2_EINVAL;
+    }
+    switch (kp) {
+        case 16: return launch_kp<16>(is_l2, tf32, tq, tx, p, grid, stream);
+        case 32: return launch_kp<32>(is_l2, tf32, tq, tx, p, grid, stream);
+        case 64: return launch_kp<64>(is_l2, tf32, tq, tx, p, grid, stream);
+        case 128: return launch_kp<128>(is_l2, tf32, tq, tx, p, grid, stream);
+        default: set_error("internal: unsupported candidate capacity %d", kp); return B2_EINVAL;
+    }
+}
+
+}  // namespace b2

@@ -1,0 +1,201 @@
+"""Vector-store boundary: the `VS` ABC of the reference (lotus/vector_store/vs.py:10-58) and `B200VS`, the
+drop-in replacement of `FaissVS` (lotus/vector_store/faiss_vs.py:13-77) backed by libb2lotus.so.
+
+    lotus.settings.configure(rm=rm, vs=B200VS())          # where the reference says vs=FaissVS()
+
+There is no CPU path: without the CUDA library / a B200 every method that computes raises.
+"""
+from __future__ import annotations
+
+import os
+from abc import ABC, abstractmethod
+from collections import OrderedDict
+from typing import Any
+
+import numpy as np
+
+from . import _native as nv
+from . import faiss_io
+from .types import RMOutput
+
+try:  # when the real package is importable, plug into ITS class hierarchy so isinstance checks pass
+    from lotus.vector_store.vs import VS as _RefVS  # type: ignore
+    from lotus.types import RMOutput as _RefRMOutput  # type: ignore
+    RMOutput = _RefRMOutput  # noqa: F811
+except Exception:  # lotus (litellm, faiss, ...) is not importable in this image: mirror the ABC
+    _RefVS = None
+
+METRIC_INNER_PRODUCT = faiss_io.METRIC_INNER_PRODUCT  # == faiss.METRIC_INNER_PRODUCT
+METRIC_L2 = faiss_io.METRIC_L2  # == faiss.METRIC_L2
+
+if _RefVS is not None:
+    VS = _RefVS
+else:
+
+    class VS(ABC):  # type: ignore[no-redef]
+        """Abstract class for vector stores (lotus/vector_store/vs.py:10-58)."""
+
+        def __init__(self) -> None:
+            self.index_dir: str | None = None
+
+        @abstractmethod
+        def index(self, docs: Any, embeddings: Any, index_dir: str, **kwargs: Any):
+            ...
+
+        @abstractmethod
+        def load_index(self, index_dir: str):
+            ...
+
+        @abstractmethod
+        def __call__(self, query_vectors: Any, K: int, ids: list[int] | None = None, **kwargs: Any) -> RMOutput:
+            ...
+
+        @abstractmethod
+        def get_vectors_from_index(self, index_dir: str, ids: list[int]) -> Any:
+            ...
+
+
+def _to_host_matrix(a: Any, want_bf16: bool):
+    """-> (array for the C-ABI, native dtype code, float32 view of the stored values)."""
+    try:
+        import torch
+        if isinstance(a, torch.Tensor):
+            t = a.detach()
+            if t.dtype == torch.bfloat16 or want_bf16:
+                bits = t.to(torch.bfloat16).contiguous().cpu().view(torch.int16).numpy().view(np.uint16)
+                return bits, nv.BF16, nv.bf16_bits_to_f32(bits)
+            f = t.to(torch.float32).contiguous().cpu().numpy()
+            return f, nv.F32, f
+    except ImportError:  # pragma: no cover
+        pass
+    f = np.ascontiguousarray(np.asarray(a), dtype=np.float32)  # faiss casts whatever it is given to float32
+    if f.ndim != 2:
+        raise ValueError(f"embeddings must be 2-D, got shape {f.shape}")
+    if want_bf16:
+        bits = nv.f32_to_bf16_bits(f)
+        return bits, nv.BF16, nv.bf16_bits_to_f32(bits)
+    return f, nv.F32, f
+
+
+class B200VS(VS):
+    """Flat (brute-force, exact) vector store on one B200.
+
+    Args mirror FaissVS(factory_string="Flat", metric=faiss.METRIC_INNER_PRODUCT) (faiss_vs.py:14).
+    dtype: "f32" (store what faiss would: float32), "bf16" (round the corpus to bfloat16 once; exact search
+    over those values), or "auto" (bf16 only when handed a bf16 tensor).
+    """
+
+    def __init__(self, factory_string: str = "Flat", metric: int = METRIC_INNER_PRODUCT, dtype: str = "auto",
+                 device: int = 0, cache_size: int = 4):
+        super().__init__()
+        if factory_string != "Flat":
+            raise ValueError(f"B200VS implements the flat (exact) index only; factory_string={factory_string!r}")
+        if metric not in (METRIC_INNER_PRODUCT, METRIC_L2):
+            raise ValueError("metric must be METRIC_INNER_PRODUCT (0) or METRIC_L2 (1)")
+        if dtype not in ("auto", "f32", "bf16"):
+            raise ValueError("dtype must be 'auto', 'f32' or 'bf16'")
+        self.factory_string = factory_string
+        self.metric = metric
+        self.dtype = dtype
+        self.device = device
+        self.index_dir: str | None = None
+        self.b2_index: nv.Index | None = None
+        self.vecs: Any = None
+        self._cache: "OrderedDict[str, tuple[float, nv.Index, Any]]" = OrderedDict()
+        self._cache_size = cache_size
+
+    # -- index lifetime ---------------------------------------------------------------------------------------------
+    def _build(self, embeddings: Any) -> nv.Index:
+        nv.require_device()
+        host, code, _ = _to_host_matrix(embeddings, self.dtype == "bf16")
+        return nv.Index(host, code, self.metric, self.device)
+
+    def _remember(self, index_dir: str, idx: nv.Index, vecs: Any) -> None:
+        key = os.path.abspath(index_dir)
+        try:
+            stamp = os.path.getmtime(f"{index_dir}/index")
+        except OSError:
+            stamp = 0.0
+        old = self._cache.pop(key, None)
+        if old is not None and old[1] is not idx:
+            old[1].close()
+        self._cache[key] = (stamp, idx, vecs)
+        while len(self._cache) > self._cache_size:
+            _, (_, victim, _) = self._cache.popitem(last=False)
+            if victim is not self.b2_index:
+                victim.close()
+
+    def index(self, docs: Any, embeddings: Any, index_dir: str, **kwargs: Any) -> None:
+        """faiss_vs.py:22-30: build the flat index, persist `vecs` (pickle) and `index` (faiss IndexFlat file)."""
+        idx = self._build(embeddings)
+        _, _, f32 = _to_host_matrix(embeddings, False)
+        faiss_io.write_index_dir(index_dir, embeddings, f32, self.metric)
+        self.b2_index = idx
+        self.vecs = embeddings
+        self.index_dir = index_dir
+        self._remember(index_dir, idx, embeddings)
+
+    def load_index(self, index_dir: str) -> None:
+        """faiss_vs.py:32-36. Directories written by FaissVS load unchanged; a device-resident copy is cached per
+        directory so operators that alternate between two indexes (sem_sim_join.py:111-127) do not rebuild."""
+        key = os.path.abspath(index_dir)
+        hit = self._cache.get(key)
+        if hit is not None:
+            try:
+                fresh = os.path.getmtime(f"{index_dir}/index") == hit[0]
+            except OSError:
+                fresh = False
+            if fresh:
+                self._cache.move_to_end(key)
+                self.index_dir, self.b2_index, self.vecs = index_dir, hit[1], hit[2]
+                return
+        vecs, x, metric = faiss_io.read_index_dir(index_dir)
+        if metric != self.metric:
+            raise ValueError(f"index at {index_dir} was built with metric {metric}, this store uses {self.metric}")
+        idx = self._build(vecs if self.dtype != "f32" else x)
+        self.index_dir, self.b2_index, self.vecs = index_dir, idx, vecs
+        self._remember(index_dir, idx, vecs)
+
+    # -- queries ----------------------------------------------------------------------------------------------------
+    def get_vectors_from_index(self, index_dir: str, ids: Any) -> np.ndarray:
+        """faiss_vs.py:38-41 (`pickle.load(vecs)[ids]`), served by the device row-gather kernel."""
+        if self.index_dir is None or os.path.abspath(index_dir) != os.path.abspath(self.index_dir):
+            self.load_index(index_dir)
+        assert self.b2_index is not None
+        ids_a = np.asarray(list(ids) if not isinstance(ids, np.ndarray) else ids, dtype=np.int64)
+        out = self.b2_index.gather(ids_a)
+        return nv.bf16_bits_to_f32(out) if self.b2_index.dtype == nv.BF16 else out
+
+    def __call__(self, query_vectors: Any, K: int, ids: list[int] | None = None, **kwargs: Any) -> RMOutput:
+        """faiss_vs.py:43-77. Returns float32 distances [Q,K] and int64 indices [Q,K] (global ids; -1 = no result).
+        The reference's wrap-around of -1 to the last id when K > len(ids) (faiss_vs.py:71-72) is NOT reproduced."""
+        if self.b2_index is None or self.index_dir is None:
+            raise ValueError("Index not loaded")
+        q, code, _ = _to_host_matrix(query_vectors, False)
+        if q.shape[1] != self.b2_index.d:
+            raise ValueError(f"query dimension {q.shape[1]} does not match the index dimension {self.b2_index.d}")
+        ids_a = None if ids is None else np.asarray(list(ids) if not isinstance(ids, np.ndarray) else ids, dtype=np.int64)
+        try:
+            distances, indices = self.b2_index.search(q, int(K), code, ids=ids_a)
+        except nv.NativeError as e:
+            if e.code in (nv.EINVAL, nv.ERANGE):
+                raise ValueError(e.msg) from e
+            raise
+        return RMOutput(distances=distances, indices=indices)
+
+    # -- extensions used by the re-registered operators --------------------------------------------------------------
+    def threshold_pairs(self, threshold: float):
+        if self.b2_index is None:
+            raise ValueError("Index not loaded")
+        return self.b2_index.threshold_pairs(threshold)
+
+    def kmeans(self, ids: Any, ncentroids: int, niter: int = 20, seed: int = 1234, full_lloyd: bool = False):
+        if self.b2_index is None:
+            raise ValueError("Index not loaded")
+        return self.b2_index.kmeans(ncentroids, niter=niter, seed=seed, ids=np.asarray(ids, dtype=np.int64), full_lloyd=full_lloyd)
+
+    def close(self) -> None:
+        for _, idx, _ in self._cache.values():
+            idx.close()
+        self._cache.clear()
+        self.b2_index = None

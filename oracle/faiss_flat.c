@@ -1,0 +1,463 @@
+/*
+ * oracle/faiss_flat.c — TEST INFRASTRUCTURE ONLY. Not part of the product; nothing under lotus_b200/
+ * may import, link or execute this file. Only tests/, __graft_entry__.smoke() and bench.py's CPU
+ * baseline legs use it, and only as the checker / the timed CPU baseline.
+ *
+ * PARITY UNPINNED: the arithmetic of the reference's hot path lives in the third-party wheel faiss-cpu
+ * (pinned `faiss-cpu>=1.8.0.post1,<2.0.0`, /root/reference/pyproject.toml:24; locked 1.13.0,
+ * /root/reference/uv.lock:573-574). It is not vendored under /root/reference, it is not installed in this
+ * image and cannot be installed (no network), and the reference's tests hold no numeric golden vectors
+ * for this path. This file therefore RESTATES the published algorithm of faiss 1.13
+ * from its public sources (file names below are upstream faiss paths) and is anchored on the reference's
+ * call sites:
+ *     faiss.index_factory(d,"Flat",metric) / Index.add / Index.search   lotus/vector_store/faiss_vs.py:23-24,63-67,75
+ *     faiss.Kmeans(d,k,niter,verbose).train ; kmeans.index.search(x,1)  lotus/utils.py:61-65
+ *     `_scores > threshold` over the all-pairs join                     lotus/sem_ops/sem_dedup.py:45-46
+ *
+ * What is restated
+ *   - IndexFlat::search -> knn_inner_product / knn_L2sqr (faiss/utils/distances.cpp) with
+ *     HeapBlockResultHandler (faiss/impl/ResultHandler.h) over faiss/utils/Heap.h heaps whose sift
+ *     comparisons use CMin/CMax::cmp2 (faiss/utils/ordered_key_value.h): admission is STRICT on the value,
+ *     eviction removes the lexicographic (value,id) extreme, heap_reorder emits best first. Database rows
+ *     are offered in ascending id (the BLAS path walks blocks j0 ascending). k == 1 uses
+ *     Top1BlockResultHandler (first best wins).
+ *   - the L2 BLAS path's ||x||^2 + ||y||^2 - 2<x,y> with negative results clamped to 0.
+ *   - Clustering::train (faiss/Clustering.cpp): subsample to k*max_points_per_centroid with
+ *     rand_perm(seed), initial centroids = first k of rand_perm(seed+1), Lloyd iterations with
+ *     compute_centroids (sums in point order, scaled by 1/count) and split_clusters (RandomGenerator(1234),
+ *     EPS = 1/1024), and faiss.Kmeans' python wrapper defaults (python/extra_wrappers.py).
+ *   - RandomGenerator = std::mt19937 (faiss/utils/random.cpp): rand_int(max) = mt() % max,
+ *     rand_float() = mt() / float(mt.max()).
+ *
+ * Scorers. sgemm's summation order is BLAS-implementation specific, so "the" fp32 score of faiss is only
+ * defined up to fp32 round-off. Three scorers are provided:
+ *   ORC_SCORER_CANONICAL (0): fp64 accumulation in a fixed order, rounded once to fp32. This is the score
+ *       the product reports bit-for-bit (include/lotus_b200.h). Order: element i belongs to accumulator
+ *       (i>>2)&31; each accumulator takes its elements in increasing i with fma; the 32 accumulators are
+ *       combined with a 16,8,4,2,1 butterfly.
+ *   ORC_SCORER_F32_SEQ (1): plain fp32 left-to-right accumulation (faiss's small-batch SIMD path has this
+ *       precision class); L2 uses the expanded BLAS form with clamp.
+ *   ORC_SCORER_F32_FAST (2): same as 1 but the compiler may vectorise/reassociate — the timed CPU baseline.
+ *
+ * Build: gcc -O3 -fopenmp -fPIC -shared (see oracle/build.py). -ffp-contract=off so that fma() calls are
+ * the only fused operations.
+ */
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_IP 0
+#define ORC_L2 1
+#define ORC_SCORER_CANONICAL 0
+#define ORC_SCORER_F32_SEQ 1
+#define ORC_SCORER_F32_FAST 2
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* scorers                                                                                                */
+/* ---------------------------------------------------------------------------------------------------- */
+
+static double butterfly32(double* acc) {
+    /* lane l ends with the same total on every lane; we only need lane 0's value. The xor-butterfly
+     * computes, at each level, t[l] = t[l] + t[l ^ off] for all l simultaneously. */
+    double t[32], u[32];
+    memcpy(t, acc, sizeof(t));
+    for (int off = 16; off >= 1; off >>= 1) {
+        for (int l = 0; l < 32; ++l) u[l] = t[l] + t[l ^ off];
+        memcpy(t, u, sizeof(t));
+    }
+    return t[0];
+}
+
+/* canonical inner product, see header comment */
+float orc_dot_canonical(const float* a, const float* b, int d) {
+    double acc[32];
+    for (int l = 0; l < 32; ++l) acc[l] = 0.0;
+    for (int i = 0; i < d; ++i) {
+        int l = (i >> 2) & 31;
+        acc[l] = fma((double)a[i], (double)b[i], acc[l]);
+    }
+    return (float)butterfly32(acc);
+}
+
+/* canonical squared L2 distance */
+float orc_l2_canonical(const float* a, const float* b, int d) {
+    double acc[32];
+    for (int l = 0; l < 32; ++l) acc[l] = 0.0;
+    for (int i = 0; i < d; ++i) {
+        int l = (i >> 2) & 31;
+        double diff = (double)a[i] - (double)b[i];
+        acc[l] = fma(diff, diff, acc[l]);
+    }
+    return (float)butterfly32(acc);
+}
+
+/* canonical squared norm as a double (used by the product's certification, exposed for tests) */
+double orc_norm2_canonical_f64(const float* a, int d) {
+    double acc[32];
+    for (int l = 0; l < 32; ++l) acc[l] = 0.0;
+    for (int i = 0; i < d; ++i) {
+        int l = (i >> 2) & 31;
+        acc[l] = fma((double)a[i], (double)a[i], acc[l]);
+    }
+    return butterfly32(acc);
+}
+
+static float dot_f32_seq(const float* a, const float* b, int d) {
+    volatile float acc = 0.f; /* volatile: forbid vectorised reassociation */
+    for (int i = 0; i < d; ++i) acc = acc + a[i] * b[i];
+    return acc;
+}
+
+static float dot_f32_fast(const float* a, const float* b, int d) {
+    float acc = 0.f;
+#pragma omp simd reduction(+ : acc)
+    for (int i = 0; i < d; ++i) acc += a[i] * b[i];
+    return acc;
+}
+
+static inline float score_pair(const float* q, const float* x, int d, int metric, int scorer, float qn, float xn) {
+    if (scorer == ORC_SCORER_CANONICAL) return metric == ORC_IP ? orc_dot_canonical(q, x, d) : orc_l2_canonical(q, x, d);
+    float ip = scorer == ORC_SCORER_F32_SEQ ? dot_f32_seq(q, x, d) : dot_f32_fast(q, x, d);
+    if (metric == ORC_IP) return ip;
+    /* faiss/utils/distances.cpp exhaustive_L2sqr_blas: dis = x_norms[i] + y_norms[j] - 2 * ip; if (dis < 0) dis = 0 */
+    float dis = qn + xn - 2 * ip;
+    if (dis < 0) dis = 0;
+    return dis;
+}
+
+/* dense score matrix out[nq,n] */
+void orc_scores(const float* x, int64_t n, int d, const float* q, int64_t nq, int metric, int scorer, float* out) {
+    float* xn = NULL;
+    if (metric == ORC_L2 && scorer != ORC_SCORER_CANONICAL) {
+        xn = (float*)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+        for (int64_t j = 0; j < n; ++j)
+            xn[j] = scorer == ORC_SCORER_F32_SEQ ? dot_f32_seq(x + j * d, x + j * d, d) : dot_f32_fast(x + j * d, x + j * d, d);
+    }
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t i = 0; i < nq; ++i) {
+        const float* qi = q + i * d;
+        float qn = 0.f;
+        if (xn) qn = scorer == ORC_SCORER_F32_SEQ ? dot_f32_seq(qi, qi, d) : dot_f32_fast(qi, qi, d);
+        for (int64_t j = 0; j < n; ++j) out[i * n + j] = score_pair(qi, x + j * d, d, metric, scorer, qn, xn ? xn[j] : 0.f);
+    }
+    free(xn);
+}
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* faiss/utils/Heap.h restated. IS_MAX = 1 -> CMax (max-heap, keeps the k smallest: L2);                  */
+/*                               IS_MAX = 0 -> CMin (min-heap, keeps the k largest: IP).                  */
+/* ---------------------------------------------------------------------------------------------------- */
+
+static inline int c_cmp(int is_max, float a, float b) { return is_max ? (a > b) : (a < b); }
+static inline int c_cmp2(int is_max, float a1, float b1, int64_t a2, int64_t b2) {
+    /* ordered_key_value.h: (a1 > b1) || ((a1 == b1) && (a2 > b2)) for CMax, same with < for CMin */
+    return is_max ? ((a1 > b1) || ((a1 == b1) && (a2 > b2))) : ((a1 < b1) || ((a1 == b1) && (a2 < b2)));
+}
+static inline float c_neutral(int is_max) { return is_max ? FLT_MAX : -FLT_MAX; }
+
+static void heap_heapify(int is_max, int k, float* val, int64_t* ids) {
+    for (int i = 0; i < k; ++i) {
+        val[i] = c_neutral(is_max);
+        ids[i] = -1;
+    }
+}
+
+/* sift the (val,id) that currently sits at 1-based position k (heap_pop) or a new (val,id) (replace_top)
+ * down from the root of a heap of size k */
+static void heap_sift_from_root(int is_max, int k, float* bh_val, int64_t* bh_ids, float val, int64_t id) {
+    bh_val--; /* 1-based */
+    bh_ids--;
+    size_t i = 1, i1, i2;
+    while (1) {
+        i1 = i << 1;
+        i2 = i1 + 1;
+        if (i1 > (size_t)k) break;
+        if (i2 == (size_t)k + 1 || c_cmp2(is_max, bh_val[i1], bh_val[i2], bh_ids[i1], bh_ids[i2])) {
+            if (c_cmp2(is_max, val, bh_val[i1], id, bh_ids[i1])) break;
+            bh_val[i] = bh_val[i1];
+            bh_ids[i] = bh_ids[i1];
+            i = i1;
+        } else {
+            if (c_cmp2(is_max, val, bh_val[i2], id, bh_ids[i2])) break;
+            bh_val[i] = bh_val[i2];
+            bh_ids[i] = bh_ids[i2];
+            i = i2;
+        }
+    }
+    bh_val[i] = val;
+    bh_ids[i] = id;
+}
+
+static void heap_replace_top(int is_max, int k, float* bh_val, int64_t* bh_ids, float val, int64_t id) {
+    heap_sift_from_root(is_max, k, bh_val, bh_ids, val, id);
+}
+
+static void heap_pop(int is_max, int k, float* bh_val, int64_t* bh_ids) {
+    /* Heap.h heap_pop: the last element is re-inserted from the root into a heap that still has k slots */
+    heap_sift_from_root(is_max, k, bh_val, bh_ids, bh_val[k - 1], bh_ids[k - 1]);
+}
+
+static void heap_reorder(int is_max, int k, float* bh_val, int64_t* bh_ids) {
+    int i, ii;
+    for (i = 0, ii = 0; i < k; i++) {
+        /* top element should be put at the end of the list */
+        float val = bh_val[0];
+        int64_t id = bh_ids[0];
+        /* boundary case: we will over-ride this value if not a true element */
+        heap_pop(is_max, k - i, bh_val, bh_ids);
+        bh_val[k - ii - 1] = val;
+        bh_ids[k - ii - 1] = id;
+        if (id != -1) ii++;
+    }
+    /* Count the number of elements which are effectively returned */
+    int nel = ii;
+    memmove(bh_val, bh_val + k - ii, (size_t)ii * sizeof(*bh_val));
+    memmove(bh_ids, bh_ids + k - ii, (size_t)ii * sizeof(*bh_ids));
+    for (; ii < k; ii++) {
+        bh_val[ii] = c_neutral(is_max);
+        bh_ids[ii] = -1;
+    }
+    (void)nel;
+}
+
+/* IndexFlat::search restated: D[nq,k], I[nq,k] */
+int orc_knn(const float* x, int64_t n, int d, const float* q, int64_t nq, int k, int metric, int scorer, float* D,
+            int64_t* I) {
+    if (k <= 0 || d <= 0) return -1;
+    const int is_max = metric == ORC_L2; /* L2 keeps the k smallest in a max-heap */
+    float* xn = NULL;
+    if (metric == ORC_L2 && scorer != ORC_SCORER_CANONICAL) {
+        xn = (float*)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+#pragma omp parallel for
+        for (int64_t j = 0; j < n; ++j)
+            xn[j] = scorer == ORC_SCORER_F32_SEQ ? dot_f32_seq(x + j * d, x + j * d, d) : dot_f32_fast(x + j * d, x + j * d, d);
+    }
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t i = 0; i < nq; ++i) {
+        const float* qi = q + i * d;
+        float* hv = D + i * k;
+        int64_t* hi = I + i * k;
+        float qn = 0.f;
+        if (xn) qn = scorer == ORC_SCORER_F32_SEQ ? dot_f32_seq(qi, qi, d) : dot_f32_fast(qi, qi, d);
+        if (k == 1) {
+            /* ResultHandler.h Top1BlockResultHandler: if (C::cmp(min_distance, distance)) replace */
+            float best = c_neutral(is_max);
+            int64_t bid = -1;
+            for (int64_t j = 0; j < n; ++j) {
+                float s = score_pair(qi, x + j * d, d, metric, scorer, qn, xn ? xn[j] : 0.f);
+                if (c_cmp(is_max, best, s)) {
+                    best = s;
+                    bid = j;
+                }
+            }
+            hv[0] = best;
+            hi[0] = bid;
+            continue;
+        }
+        heap_heapify(is_max, k, hv, hi);
+        float thresh = hv[0];
+        for (int64_t j = 0; j < n; ++j) {
+            float s = score_pair(qi, x + j * d, d, metric, scorer, qn, xn ? xn[j] : 0.f);
+            /* HeapBlockResultHandler::add_results: if (C::cmp(thresh, dis)) { heap_replace_top; thresh = top } */
+            if (c_cmp(is_max, thresh, s)) {
+                heap_replace_top(is_max, k, hv, hi, s, j);
+                thresh = hv[0];
+            }
+        }
+        heap_reorder(is_max, k, hv, hi);
+    }
+    free(xn);
+    return 0;
+}
+
+/* all pairs i<j with canonical IP score > thr (strict). Returns the number found; writes up to cap. */
+int64_t orc_threshold_pairs(const float* x, int64_t n, int d, float thr, int64_t* out_i, int64_t* out_j, int64_t cap) {
+    int64_t cnt = 0;
+    for (int64_t i = 0; i < n; ++i)
+        for (int64_t j = i + 1; j < n; ++j) {
+            float s = orc_dot_canonical(x + i * d, x + j * d, d);
+            if (s > thr) {
+                if (cnt < cap) {
+                    out_i[cnt] = i;
+                    out_j[cnt] = j;
+                }
+                cnt++;
+            }
+        }
+    return cnt;
+}
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* std::mt19937 (32-bit Mersenne Twister, the generator behind faiss::RandomGenerator)                   */
+/* ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+    uint32_t mt[624];
+    int idx;
+} orc_mt19937;
+
+void orc_mt_seed(orc_mt19937* g, uint32_t seed) {
+    g->mt[0] = seed;
+    for (int i = 1; i < 624; ++i) g->mt[i] = 1812433253u * (g->mt[i - 1] ^ (g->mt[i - 1] >> 30)) + (uint32_t)i;
+    g->idx = 624;
+}
+
+uint32_t orc_mt_next(orc_mt19937* g) {
+    if (g->idx >= 624) {
+        for (int i = 0; i < 624; ++i) {
+            uint32_t y = (g->mt[i] & 0x80000000u) | (g->mt[(i + 1) % 624] & 0x7fffffffu);
+            g->mt[i] = g->mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        g->idx = 0;
+    }
+    uint32_t y = g->mt[g->idx++];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+
+/* first `count` outputs of mt19937(seed) (known-answer tests) */
+void orc_mt_fill(uint32_t seed, uint32_t* out, int count) {
+    orc_mt19937 g;
+    orc_mt_seed(&g, seed);
+    for (int i = 0; i < count; ++i) out[i] = orc_mt_next(&g);
+}
+
+/* faiss/utils/random.cpp rand_perm: Fisher-Yates with rand_int(n - i) = mt() % (n - i) */
+void orc_rand_perm(int32_t* perm, int64_t n, int64_t seed) {
+    for (int64_t i = 0; i < n; i++) perm[i] = (int32_t)i;
+    orc_mt19937 g;
+    orc_mt_seed(&g, (uint32_t)seed);
+    for (int64_t i = 0; i + 1 < n; i++) {
+        int i2 = (int)(i + (int64_t)(orc_mt_next(&g) % (uint32_t)(n - i)));
+        int32_t t = perm[i];
+        perm[i] = perm[i2];
+        perm[i2] = t;
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* faiss/Clustering.cpp restated                                                                         */
+/* ---------------------------------------------------------------------------------------------------- */
+
+/* compute_centroids: sums in point order, then scale by 1/count (float) */
+void orc_compute_centroids(int d, int k, int64_t n, const float* x, const int64_t* assign, float* hassign,
+                           float* centroids) {
+    memset(hassign, 0, sizeof(float) * (size_t)k);
+    memset(centroids, 0, sizeof(float) * (size_t)k * d);
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t ci = assign[i];
+        float* c = centroids + ci * d;
+        const float* xi = x + i * d;
+        hassign[ci] += 1.0f;
+        for (int j = 0; j < d; ++j) c[j] += xi[j];
+    }
+    for (int ci = 0; ci < k; ++ci) {
+        if (hassign[ci] == 0) continue;
+        float norm = 1 / hassign[ci];
+        float* c = centroids + (size_t)ci * d;
+        for (int j = 0; j < d; ++j) c[j] *= norm;
+    }
+}
+
+/* split_clusters: EPS = 1/1024, RandomGenerator rng(1234) */
+int orc_split_clusters(int d, int k, int64_t n, float* hassign, float* centroids) {
+    const double EPS = 1 / 1024.;
+    int nsplit = 0;
+    orc_mt19937 g;
+    orc_mt_seed(&g, 1234u);
+    for (int ci = 0; ci < k; ci++) {
+        if (hassign[ci] == 0) { /* need to redefine a centroid */
+            int cj;
+            for (cj = 0; 1; cj = (cj + 1) % k) {
+                /* probability to pick this cluster for split */
+                float p = (hassign[cj] - 1.0) / (float)(n - k);
+                float r = orc_mt_next(&g) / (float)4294967295u; /* mt() / float(mt.max()) */
+                if (r < p) break; /* found our cluster to be split */
+            }
+            memcpy(centroids + (size_t)ci * d, centroids + (size_t)cj * d, sizeof(*centroids) * (size_t)d);
+            /* small symmetric pertubation */
+            for (int j = 0; j < d; j++) {
+                if (j % 2 == 0) {
+                    centroids[(size_t)ci * d + j] *= 1 + EPS;
+                    centroids[(size_t)cj * d + j] *= 1 - EPS;
+                } else {
+                    centroids[(size_t)ci * d + j] *= 1 - EPS;
+                    centroids[(size_t)cj * d + j] *= 1 + EPS;
+                }
+            }
+            /* assume even split of the cluster */
+            hassign[ci] = hassign[cj] / 2;
+            hassign[cj] -= hassign[ci];
+            nsplit++;
+        }
+    }
+    return nsplit;
+}
+
+/* faiss.Kmeans(d,k,niter=niter).train(x) + index.search(x,1).
+ * x[n,d]; out_assign[n]; out_centroids[k,d]; out_obj[niter] (sum of the reported distances per iteration).
+ * max_points_per_centroid = 256 (ClusteringParameters default), seed = 1234, nredo = 1. full_lloyd != 0
+ * disables the subsampling. Returns 0, or -1 when n < k (faiss throws). */
+int orc_kmeans(const float* x, int64_t n, int d, int k, int niter, int64_t seed, int scorer, int full_lloyd,
+               int64_t* out_assign, float* out_centroids, float* out_obj) {
+    if (n < k || k <= 0) return -1;
+    const int max_points_per_centroid = 256;
+    const float* xt = x;
+    float* xsub = NULL;
+    int64_t nx = n;
+    if (!full_lloyd && nx > (int64_t)k * max_points_per_centroid) {
+        /* subsample_training_set: perm = rand_perm(nx, seed); keep the first k*max_points */
+        int32_t* perm = (int32_t*)malloc(sizeof(int32_t) * (size_t)nx);
+        orc_rand_perm(perm, nx, seed);
+        nx = (int64_t)k * max_points_per_centroid;
+        xsub = (float*)malloc(sizeof(float) * (size_t)nx * d);
+        for (int64_t i = 0; i < nx; ++i) memcpy(xsub + i * d, x + (int64_t)perm[i] * d, sizeof(float) * (size_t)d);
+        free(perm);
+        xt = xsub;
+    }
+    float* centroids = out_centroids;
+    if (nx == k) {
+        /* "Number of training points same as number of centroids, just copying" */
+        memcpy(centroids, xt, sizeof(float) * (size_t)k * d);
+    } else {
+        int32_t* perm = (int32_t*)malloc(sizeof(int32_t) * (size_t)nx);
+        orc_rand_perm(perm, nx, seed + 1); /* seed + 1 + redo * 15486557L, redo = 0 */
+        for (int i = 0; i < k; ++i) memcpy(centroids + (size_t)i * d, xt + (int64_t)perm[i] * d, sizeof(float) * (size_t)d);
+        free(perm);
+        int64_t* assign = (int64_t*)malloc(sizeof(int64_t) * (size_t)nx);
+        float* dis = (float*)malloc(sizeof(float) * (size_t)nx);
+        float* hassign = (float*)malloc(sizeof(float) * (size_t)k);
+        for (int it = 0; it < niter; ++it) {
+            orc_knn(centroids, k, d, xt, nx, 1, ORC_L2, scorer, dis, assign);
+            double obj = 0;
+            for (int64_t i = 0; i < nx; ++i) obj += dis[i];
+            if (out_obj) out_obj[it] = (float)obj;
+            orc_compute_centroids(d, k, nx, xt, assign, hassign, centroids);
+            orc_split_clusters(d, k, nx, hassign, centroids);
+        }
+        free(assign);
+        free(dis);
+        free(hassign);
+    }
+    free(xsub);
+    /* lotus/utils.py:65 kmeans.index.search(vec_set, 1) over ALL points */
+    float* dis_all = (float*)malloc(sizeof(float) * (size_t)n);
+    orc_knn(centroids, k, d, x, n, 1, ORC_L2, scorer, dis_all, out_assign);
+    free(dis_all);
+    return 0;
+}
