@@ -7,7 +7,7 @@
 #include <mutex>
 #include <vector>
 
-#include "common.cuh"
+#include "index.cuh"
 
 namespace b2 {
 
@@ -23,102 +23,20 @@ void set_error(const char* fmt, ...) {
     g_err = buf;
 }
 
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    int ensure(size_t bytes) {
-        if (bytes <= cap) return B2_OK;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
-            p = nullptr;
-            return B2_ENOMEM;
-        }
-        cap = want;
-        return B2_OK;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-    template <typename T>
-    T* as() { return reinterpret_cast<T*>(p); }
-};
-
-struct HostBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    int ensure(size_t bytes) {
-        if (bytes <= cap) return B2_OK;
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        cap = 0;
-        cudaError_t e = cudaMallocHost(&p, bytes + 256);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            set_error("cudaMallocHost(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
-            return B2_ENOMEM;
-        }
-        cap = bytes + 256;
-        return B2_OK;
-    }
-    void release() {
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
-
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-        else prev = -1;
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-
 }  // namespace b2
 
 using namespace b2;
 
-struct b2_index {
-    int device = 0;
-    int64_t n = 0;
-    int32_t d = 0;
-    int32_t dtype = B2_F32;
-    int32_t metric = B2_METRIC_IP;
-    DevBuf store, filt_pad, norm2, scalar;
-    MatView view;
-    // per-call workspaces
-    DevBuf q_in, q_filt, cand_score, cand_id, cand_thr, flags, sel, dense, out_sc, out_id, ids_dev;
-    DevBuf sub_store, sub_filt, sub_norm2;
-    HostBuf h_flags;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    float last_filter_ms = -1.f;
-};
-
 namespace b2 {
 
-static size_t esize(int dtype) { return dtype == B2_F32 ? 4 : 2; }
-
 // Build the searchable view of a row-major matrix that already sits in device memory.
-static int build_view(const void* store, int64_t n, int d, int dtype, DevBuf& filt_pad, DevBuf& norm2, DevBuf& scalar,
+int build_view(const void* store, int64_t n, int d, int dtype, DevBuf& filt_pad, DevBuf& norm2, DevBuf& scalar,
                       MatView& v, cudaStream_t st) {
     v.store = store;
     v.n = n;
     v.d = d;
     v.dtype = dtype;
+    v.filt_dtype = dtype;
     const int align = dtype == B2_F32 ? 4 : 8;  // TMA row pitch must be a multiple of 16 bytes
     if (d % align == 0) {
         v.filt = store;
@@ -141,17 +59,19 @@ static int build_view(const void* store, int64_t n, int d, int dtype, DevBuf& fi
 }
 
 // relative (to ||q||*||x||) bound on |filter score - exact score| of the inner product
-static float filter_rel_eps(int index_dtype, int q_dtype, int d) {
+float filter_rel_eps(int store_dtype, int filt_dtype, int q_dtype, int d) {
     // fp32 accumulation inside the tensor core: products are exact, every accumulation step may lose one
     // (truncated) ulp of the running magnitude; (d + 64) * 2^-23 is generous (validated in tests/test_gpu_filter.py)
-    double acc = (double)(d + 64) * 1.1920929e-7;
-    double conv = 0.0;
-    if (index_dtype == B2_F32) {
-        conv = 2.0 * 9.765625e-4 + 1e-6;  // both operands truncated to TF32 (10 explicit mantissa bits)
-    } else if (q_dtype == B2_F32) {
-        conv = 3.90625e-3 + 1e-6;  // queries rounded to bf16 for the filter (index values are exact)
+    const double acc = (double)(d + 64) * 1.1920929e-7;
+    double ex = 0.0, eq = 0.0;  // relative representation error of the corpus / query operand seen by the MMA
+    if (filt_dtype == B2_F32) {  // kind::tf32 keeps 10 explicit mantissa bits of an fp32 operand
+        ex = store_dtype == B2_F32 ? 9.765625e-4 : 0.0;  // bf16 values are exact in tf32
+        eq = q_dtype == B2_F32 ? 9.765625e-4 : 0.0;
+    } else {  // kind::f16 on bf16 operands
+        ex = store_dtype == B2_F32 ? 3.90625e-3 : 0.0;  // fp32 values rounded to bf16 for the filter
+        eq = q_dtype == B2_F32 ? 3.90625e-3 : 0.0;
     }
-    return (float)(acc + conv);
+    return (float)(acc + ex + eq + ex * eq + 1e-6);
 }
 
 __global__ void fill_pad_kernel(float* sc, int64_t* id, int64_t total, float pad) {
@@ -161,12 +81,11 @@ __global__ void fill_pad_kernel(float* sc, int64_t* id, int64_t total, float pad
     }
 }
 
-static int search_core(b2_index* idx, const MatView& X, const void* q_dev, int q_dtype, int64_t nq, int k,
+int search_core(b2_index* idx, const MatView& X, int metric, const void* q_dev, int q_dtype, int64_t nq, int k,
                        const int64_t* id_map, int64_t id_offset, float* out_sc, int64_t* out_id, cudaStream_t st) {
     idx->last_filter_ms = -1.f;
     if (nq <= 0) return B2_OK;
     g_stats[ST_QUERIES] += nq;
-    const int metric = idx->metric;
     if (X.n <= 0) {
         fill_pad_kernel<<<148, 256, 0, st>>>(out_sc, out_id, nq * k, metric == B2_METRIC_L2 ? FLT_MAX : -FLT_MAX);
         B2_LAUNCH_CHECK();
@@ -189,9 +108,11 @@ static int search_core(b2_index* idx, const MatView& X, const void* q_dev, int q
     }
     int dev_sms = 148;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, idx->device);
-    const int filt_dtype = X.dtype;
+    const int filt_dtype = X.filt_dtype;
     const int64_t q_pitch = round_up(X.d, filt_dtype == B2_F32 ? 4 : 8);
-    const float rel_eps = filter_rel_eps(X.dtype, q_dtype, X.d);
+    const float rel_eps = filter_rel_eps(X.dtype, filt_dtype, q_dtype, X.d);
+    // queries that already have the filter's element type and a TMA-compatible pitch are streamed in place
+    const bool q_in_place = q_dtype == filt_dtype && q_pitch == X.d && (reinterpret_cast<uintptr_t>(q_dev) & 15) == 0;
     // bound the candidate workspace: process the queries in chunks
     const int64_t chunk = 1 << 20;
     for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
@@ -200,15 +121,16 @@ static int search_core(b2_index* idx, const MatView& X, const void* q_dev, int q
         float* osc = out_sc + (size_t)q0 * k;
         int64_t* oid = out_id + (size_t)q0 * k;
         const int n_splits = filter_choose_splits(nqc, X.n, dev_sms);
-        B2_TRY(idx->q_filt.ensure((size_t)nqc * q_pitch * esize(filt_dtype)));
+        if (!q_in_place) B2_TRY(idx->q_filt.ensure((size_t)nqc * q_pitch * esize(filt_dtype)));
+        const void* q_filt = q_in_place ? static_cast<const void*>(qc) : idx->q_filt.p;
         B2_TRY(idx->cand_score.ensure((size_t)nqc * n_splits * kp * sizeof(float)));
         B2_TRY(idx->cand_id.ensure((size_t)nqc * n_splits * kp * sizeof(int32_t)));
         B2_TRY(idx->cand_thr.ensure((size_t)nqc * n_splits * sizeof(float)));
         B2_TRY(idx->flags.ensure((size_t)nqc * sizeof(int32_t)));
         B2_TRY(idx->h_flags.ensure((size_t)nqc * sizeof(int32_t)));
-        B2_TRY(launch_prep_queries(qc, q_dtype, nqc, X.d, idx->q_filt.p, filt_dtype, q_pitch, st));
+        if (!q_in_place) B2_TRY(launch_prep_queries(qc, q_dtype, nqc, X.d, idx->q_filt.p, filt_dtype, q_pitch, st));
         B2_CUDA(cudaEventRecord(idx->ev0, st));
-        B2_TRY(launch_knn_filter(X, idx->q_filt.p, q_pitch, nqc, metric, kp, n_splits, idx->cand_score.as<float>(),
+        B2_TRY(launch_knn_filter(X, q_filt, q_pitch, nqc, metric, kp, n_splits, idx->cand_score.as<float>(),
                                  idx->cand_id.as<int32_t>(), idx->cand_thr.as<float>(), idx->device, st));
         B2_CUDA(cudaEventRecord(idx->ev1, st));
         B2_TRY(launch_finalize(X, qc, q_dtype, nqc, metric, k, kp, n_splits, idx->cand_score.as<float>(),
@@ -322,6 +244,12 @@ int b2_index_create(const void* x, int64_t n, int32_t d, int32_t dtype, int32_t 
     int rc = idx->store.ensure(bytes);
     if (rc != B2_OK) return fail(rc);
     if (n > 0) {
+        // a device-resident source was produced on some other stream (e.g. torch's): our private stream is
+        // non-blocking, so order the copy after everything already submitted to the device
+        if (x_on_device && cudaDeviceSynchronize() != cudaSuccess) {
+            set_error("device synchronisation before the copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return fail(B2_ECUDA);
+        }
         cudaError_t e = cudaMemcpyAsync(idx->store.p, x, (size_t)n * d * esize(dtype),
                                         x_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, idx->stream);
         if (e != cudaSuccess) { set_error("copy of the matrix failed: %s", cudaGetErrorString(e)); return fail(B2_ECUDA); }
@@ -374,9 +302,9 @@ int b2_index_search_dev(b2_index* idx, const void* q_dev, int64_t nq, int32_t q_
         if (n_ids < 0) { set_error("n_ids < 0"); return B2_EINVAL; }
         MatView sub;
         B2_TRY(build_subset(idx, ids_dev, n_ids, sub, st));
-        B2_TRY(search_core(idx, sub, q_dev, q_dtype, nq, k, ids_dev, 0, out_scores_dev, out_idx_dev, st));
+        B2_TRY(search_core(idx, sub, idx->metric, q_dev, q_dtype, nq, k, ids_dev, 0, out_scores_dev, out_idx_dev, st));
     } else {
-        B2_TRY(search_core(idx, idx->view, q_dev, q_dtype, nq, k, nullptr, id_offset, out_scores_dev, out_idx_dev, st));
+        B2_TRY(search_core(idx, idx->view, idx->metric, q_dev, q_dtype, nq, k, nullptr, id_offset, out_scores_dev, out_idx_dev, st));
     }
     B2_CUDA(cudaStreamSynchronize(st));
     return B2_OK;
@@ -408,9 +336,9 @@ int b2_index_search(b2_index* idx, const void* q, int64_t nq, int32_t q_dtype, i
     if (ids_dev) {
         MatView sub;
         B2_TRY(build_subset(idx, ids_dev, n_ids, sub, st));
-        B2_TRY(search_core(idx, sub, idx->q_in.p, q_dtype, nq, k, ids_dev, 0, idx->out_sc.as<float>(), idx->out_id.as<int64_t>(), st));
+        B2_TRY(search_core(idx, sub, idx->metric, idx->q_in.p, q_dtype, nq, k, ids_dev, 0, idx->out_sc.as<float>(), idx->out_id.as<int64_t>(), st));
     } else {
-        B2_TRY(search_core(idx, idx->view, idx->q_in.p, q_dtype, nq, k, nullptr, 0, idx->out_sc.as<float>(),
+        B2_TRY(search_core(idx, idx->view, idx->metric, idx->q_in.p, q_dtype, nq, k, nullptr, 0, idx->out_sc.as<float>(),
                            idx->out_id.as<int64_t>(), st));
     }
     B2_CUDA(cudaMemcpyAsync(out_scores, idx->out_sc.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));

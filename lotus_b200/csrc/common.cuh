@@ -87,7 +87,8 @@ struct MatView {
     const float* norm2 = nullptr;  // [n] fp32 squared norms of the exact rows (L2 filter epilogue)
     int64_t n = 0;
     int32_t d = 0;
-    int32_t dtype = B2_F32;
+    int32_t dtype = B2_F32;       // element type of `store`
+    int32_t filt_dtype = B2_F32;  // element type of `filt`: B2_BF16 -> kind::f16 MMA, B2_F32 -> kind::tf32 MMA
     int64_t filt_pitch = 0;  // elements
     float max_norm = 0.f;    // max_j ||x_j|| (upper bound), for the certification margin
 };
@@ -101,6 +102,8 @@ int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int
                       int n_splits, float* cand_score, int32_t* cand_id, float* cand_thr, int device,
                       cudaStream_t stream);
 int filter_choose_splits(int64_t nq, int64_t n, int num_sms);
+int launch_pair_filter(const MatView& X, float thr, int part, int nparts, int32_t* pair_i, int32_t* pair_j,
+                       unsigned long long* pair_count, unsigned long long cap, int device, cudaStream_t stream);
 
 // knn_exact.cu
 int launch_prep_queries(const void* q, int q_dtype, int64_t nq, int d, void* q_filt, int filt_dtype,

@@ -36,7 +36,8 @@ constexpr int EPI_WARP0 = 4;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_LIMIT = 232448;  // 227 KB
 
-__host__ __device__ constexpr int list_bytes(int kp) { return kp * BLOCK_M * 8; }
+constexpr int PEND = 16;  // pending (not yet merged) candidates per query row between lockstep flushes
+__host__ __device__ constexpr int list_bytes(int kp) { return (kp + PEND) * BLOCK_M * 8; }
 __host__ __device__ constexpr int misc_bytes() { return 2 * BLOCK_N * 4 /*xnorm*/ + 256 /*barriers*/; }
 __host__ __device__ constexpr int num_stages(int kp) {
     int s = (SMEM_LIMIT - list_bytes(kp) - misc_bytes()) / STAGE_BYTES;
@@ -61,6 +62,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
     uint32_t spins = 0;
+    long long t_start = 0;
     while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -70,9 +72,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) break;
-        if (++spins > (1u << 26)) {  // each failed try_wait already blocks for a HW time slice; this is seconds
-            printf("b2 knn_filter: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
+        if ((++spins & 0x3ffu) == 0) {
+            const long long now = clock64();
+            if (t_start == 0) t_start = now;
+            else if (now - t_start > 8000000000LL) {  // ~4 s at 2 GHz: no legitimate wait is longer than microseconds
+                printf("b2 knn_filter: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+                __trap();
+            }
         }
     }
 }
@@ -166,25 +172,196 @@ struct FilterParams {
     int32_t n_splits;
     int32_t tiles_per_split;  // corpus tiles (of 256 rows) per split
     int32_t n_ntiles;         // ceil(n / 256)
+    // all-pairs (dedup) schedule: the query matrix IS the corpus; item i is query tile part + i*nparts and sweeps
+    // only the corpus tiles that can hold a column j > i (upper triangle)
+    int32_t pair_mode, part, nparts;
+    float pair_thr;                   // emit candidates with filter score > pair_thr
+    int32_t* pair_i;                  // [pair_cap]
+    int32_t* pair_j;
+    unsigned long long* pair_count;   // total candidates found (may exceed pair_cap)
+    unsigned long long pair_cap;
 };
 
-// Replace-min insertion into the thread's candidate list (column `row` of sc/id, stride BLOCK_M).
-// Returns the new threshold (min of the list; -inf while a slot is free) and its position.
+struct Ring {
+    uint8_t* stage_base;
+    uint64_t *full_bar, *empty_bar, *tmem_full, *tmem_empty;
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ int num_items(const FilterParams& p) {
+    if (p.pair_mode) return p.n_mtiles > p.part ? (p.n_mtiles - p.part + p.nparts - 1) / p.nparts : 0;
+    return p.n_mtiles * p.n_splits;
+}
+__device__ __forceinline__ void item_range(const FilterParams& p, int item, int& m_tile, int& split, int& t0, int& t1) {
+    if (p.pair_mode) {
+        m_tile = p.part + item * p.nparts;
+        split = 0;
+        t0 = (m_tile * BLOCK_M) / BLOCK_N;  // first corpus tile that can contain a column > row
+        t1 = p.n_ntiles;
+    } else {
+        m_tile = item % p.n_mtiles;
+        split = item / p.n_mtiles;
+        t0 = split * p.tiles_per_split;
+        t1 = min(t0 + p.tiles_per_split, p.n_ntiles);
+    }
+}
+
+// TMA producer: one elected lane streams (query tile, corpus tile) K-blocks into the smem ring.
+template <bool TF32, int NSTAGES>
+__device__ __forceinline__ void producer_loop(const CUtensorMap* tmap_q, const CUtensorMap* tmap_x, const FilterParams& p,
+                                              const Ring& r) {
+    constexpr int KB_ELEMS = TF32 ? 32 : 64;  // elements per 128-byte K-block row
+    const int n_items = num_items(p);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int m_tile, split, t0, t1;
+        item_range(p, item, m_tile, split, t0, t1);
+        for (int t = t0; t < t1; ++t) {
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(&r.empty_bar[stage], phase ^ 1);
+                uint8_t* sa = r.stage_base + stage * STAGE_BYTES;
+                uint8_t* sb = sa + STAGE_A_BYTES;
+                mbar_arrive_expect_tx(&r.full_bar[stage], STAGE_BYTES);
+                tma_load_2d(sa, tmap_q, &r.full_bar[stage], kb * KB_ELEMS, m_tile * BLOCK_M);
+                tma_load_2d(sb, tmap_x, &r.full_bar[stage], kb * KB_ELEMS, t * BLOCK_N);
+                if (++stage == NSTAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    }
+}
+
+// MMA issuer: one elected lane issues tcgen05.mma for every K-block, accumulating a 128x256 fp32 tile in TMEM.
+template <bool TF32, int NSTAGES>
+__device__ __forceinline__ void mma_loop(const FilterParams& p, const Ring& r) {
+    constexpr uint32_t idesc = make_idesc<TF32>();
+    const int n_items = num_items(p);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int m_tile, split, t0, t1;
+        item_range(p, item, m_tile, split, t0, t1);
+        for (int t = t0; t < t1; ++t) {
+            mbar_wait(&r.tmem_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = r.tmem_base + acc * BLOCK_N;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(&r.full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(r.stage_base + stage * STAGE_BYTES);
+                const uint64_t adesc = make_sw128_desc(sa);
+                const uint64_t bdesc = make_sw128_desc(sa + STAGE_A_BYTES);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // +32 bytes per UMMA_K step inside the 128-byte swizzle row (start address is in 16 B units)
+                    tc_mma<TF32>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                tc_commit(&r.empty_bar[stage]);  // frees the smem stage when these MMAs retire
+                if (++stage == NSTAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            tc_commit(&r.tmem_full[acc]);  // accumulator complete -> epilogue
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+}
+
+// barrier init + TMEM allocation shared by both kernels; returns after the block-wide sync
+template <int NSTAGES>
+__device__ __forceinline__ Ring setup_ring(uint8_t* smem, uint64_t* bars, const CUtensorMap* tmap_q, const CUtensorMap* tmap_x) {
+    Ring r;
+    r.stage_base = smem;
+    r.full_bar = bars;
+    r.empty_bar = bars + NSTAGES;
+    r.tmem_full = bars + 2 * NSTAGES;
+    r.tmem_empty = r.tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(r.tmem_empty + 2);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if ((smem_u32(smem) & 1023u) != 0) {
+        if (threadIdx.x == 0) printf("b2 knn_filter: dynamic smem base not 1024-aligned\n");
+        __trap();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(tmap_q);
+        tma_prefetch_desc(tmap_x);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < NSTAGES; ++s) {
+            mbar_init(&r.full_bar[s], 1);
+            mbar_init(&r.empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&r.tmem_full[a], 1);
+            mbar_init(&r.tmem_empty[a], 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    r.tmem_base = *tmem_ptr;
+    return r;
+}
+
+__device__ __forceinline__ void teardown_ring(const Ring& r) {
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 2) {
+        tc_fence_after();
+        tmem_dealloc(r.tmem_base, TMEM_COLS);
+    }
+}
+
+// Replace-min insertion into the thread's candidate list (column `row` of sc/id, stride BLOCK_M): overwrite
+// the current minimum, then rescan for the new minimum (= threshold; -inf while a slot is free).
+// Called only from flush_pending, where all 32 lanes of the warp run it in lockstep.
 template <int KP>
-__device__ __noinline__ float2 list_insert(float* sc, int32_t* id, float s, int32_t idx, int minpos) {
+__device__ __forceinline__ void list_insert(float* sc, int32_t* id, float s, int32_t idx, float& thr, int& minpos) {
     sc[minpos * BLOCK_M] = s;
     id[minpos * BLOCK_M] = idx;
     float m = sc[0];
     int mp = 0;
 #pragma unroll 8
     for (int p = 1; p < KP; ++p) {
-        float v = sc[p * BLOCK_M];
+        const float v = sc[p * BLOCK_M];
         if (v < m) {
             m = v;
             mp = p;
         }
     }
-    return make_float2(m, __int_as_float(mp));
+    thr = m;
+    minpos = mp;
+}
+
+// Merge every lane's pending candidates into its list. Warp-collective: the loop bound is the warp-wide
+// maximum so the 32 lanes (32 different queries) execute their insertions together instead of one lane at a
+// time (the divergent version of this cost ~20x more issue slots).
+template <int KP>
+__device__ __forceinline__ void flush_pending(float* my_sc, int32_t* my_id, const float* pend_sc, const int32_t* pend_id,
+                                              int& cnt, float& thr, int& minpos) {
+    int mx = cnt;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    for (int i = 0; i < mx; ++i) {
+        if (i < cnt) {
+            const float s = pend_sc[i * BLOCK_M];
+            if (s > thr) list_insert<KP>(my_sc, my_id, s, pend_id[i * BLOCK_M], thr, minpos);
+        }
+        __syncwarp();
+    }
+    cnt = 0;
 }
 
 template <int KP, bool IS_L2, bool TF32>
@@ -199,113 +376,22 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     uint8_t* stage_base = smem;
     float* list_sc = reinterpret_cast<float*>(smem + NSTAGES * STAGE_BYTES);
     int32_t* list_id = reinterpret_cast<int32_t*>(list_sc + KP * BLOCK_M);
-    float* s_xn = reinterpret_cast<float*>(list_id + KP * BLOCK_M);  // [2][BLOCK_N]
+    float* pend_sc_base = reinterpret_cast<float*>(list_id + KP * BLOCK_M);     // [PEND][BLOCK_M]
+    int32_t* pend_id_base = reinterpret_cast<int32_t*>(pend_sc_base + PEND * BLOCK_M);
+    float* s_xn = reinterpret_cast<float*>(pend_id_base + PEND * BLOCK_M);  // [2][BLOCK_N]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_xn + 2 * BLOCK_N);
-    uint64_t* full_bar = bars;                 // [NSTAGES]
-    uint64_t* empty_bar = bars + NSTAGES;      // [NSTAGES]
-    uint64_t* tmem_full = bars + 2 * NSTAGES;  // [2]
-    uint64_t* tmem_empty = tmem_full + 2;      // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-
-    if ((smem_u32(smem) & 1023u) != 0) {
-        if (threadIdx.x == 0) printf("b2 knn_filter: dynamic smem base not 1024-aligned\n");
-        __trap();
-    }
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmap_q);
-        tma_prefetch_desc(&tmap_x);
-    }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < NSTAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-        }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
-        }
-        fence_barrier_init();
-    }
-    if (warp == 2) tmem_alloc(tmem_ptr, TMEM_COLS);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-
-    const int n_items = p.n_mtiles * p.n_splits;
+    const Ring ring = setup_ring<NSTAGES>(smem, bars, &tmap_q, &tmap_x);
+    uint64_t* tmem_full = ring.tmem_full;
+    uint64_t* tmem_empty = ring.tmem_empty;
+    const uint32_t tmem_base = ring.tmem_base;
+    const int n_items = num_items(p);
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int m_tile = item % p.n_mtiles;
-                const int split = item / p.n_mtiles;
-                const int t0 = split * p.tiles_per_split;
-                const int t1 = min(t0 + p.tiles_per_split, p.n_ntiles);
-                for (int t = t0; t < t1; ++t) {
-                    for (int kb = 0; kb < p.num_kb; ++kb) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        uint8_t* sa = stage_base + stage * STAGE_BYTES;
-                        uint8_t* sb = sa + STAGE_A_BYTES;
-                        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-                        tma_load_2d(sa, &tmap_q, &full_bar[stage], kb * KB_ELEMS, m_tile * BLOCK_M);
-                        tma_load_2d(sb, &tmap_x, &full_bar[stage], kb * KB_ELEMS, t * BLOCK_N);
-                        if (++stage == NSTAGES) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                    }
-                }
-            }
-        }
+        if (lane == 0) producer_loop<TF32, NSTAGES>(&tmap_q, &tmap_x, p, ring);
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc<TF32>();
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int split = item / p.n_mtiles;
-                const int t0 = split * p.tiles_per_split;
-                const int t1 = min(t0 + p.tiles_per_split, p.n_ntiles);
-                for (int t = t0; t < t1; ++t) {
-                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-                    tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-                    for (int kb = 0; kb < p.num_kb; ++kb) {
-                        mbar_wait(&full_bar[stage], phase);
-                        tc_fence_after();
-                        const uint32_t sa = smem_u32(stage_base + stage * STAGE_BYTES);
-                        const uint64_t adesc = make_sw128_desc(sa);
-                        const uint64_t bdesc = make_sw128_desc(sa + STAGE_A_BYTES);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            // +32 bytes per UMMA_K step inside the 128-byte swizzle row (start address is in 16 B units)
-                            tc_mma<TF32>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                         (kb | k) != 0 ? 1u : 0u);
-                        }
-                        tc_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
-                        if (++stage == NSTAGES) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                    }
-                    tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
-                    if (++acc == 2) {
-                        acc = 0;
-                        acc_phase ^= 1;
-                    }
-                }
-            }
-        }
+        if (lane == 0) mma_loop<TF32, NSTAGES>(p, ring);
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue: streaming top-KP per query row =====================
         const int quad = warp - EPI_WARP0;   // == warp % 4: the TMEM lane quarter this warp may read
@@ -313,13 +399,13 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         const int epi_tid = threadIdx.x - EPI_WARP0 * 32;
         float* my_sc = list_sc + row;
         int32_t* my_id = list_id + row;
+        float* pend_sc = pend_sc_base + row;
+        int32_t* pend_id = pend_id_base + row;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int m_tile = item % p.n_mtiles;
-            const int split = item / p.n_mtiles;
-            const int t0 = split * p.tiles_per_split;
-            const int t1 = min(t0 + p.tiles_per_split, p.n_ntiles);
+            int m_tile, split, t0, t1;
+            item_range(p, item, m_tile, split, t0, t1);
 #pragma unroll 4
             for (int i = 0; i < KP; ++i) {
                 my_sc[i * BLOCK_M] = -INFINITY;
@@ -327,6 +413,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             }
             float thr = -INFINITY;
             int minpos = 0;
+            int cnt = 0;  // pending candidates of this row
             for (int t = t0; t < t1; ++t) {
                 const int col0 = t * BLOCK_N;
                 if constexpr (IS_L2) {
@@ -374,16 +461,29 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     float mx = v[0];
 #pragma unroll
                     for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
-                    if (mx > thr) {
-                        const int idx0 = col0 + c * 32;
+                    if (!__any_sync(0xffffffffu, mx > thr)) continue;  // nothing in this 32x32 block beats any row's threshold
+                    const int idx0 = col0 + c * 32;
+                    int j_start = 0;
+                    while (true) {  // warp-uniform loop; a second trip only after a buffer overflowed mid-chunk
+                        int lost_at = 32;
+                        if (mx > thr) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (v[j] > thr) {
-                                const float2 r = list_insert<KP>(my_sc, my_id, v[j], idx0 + j, minpos);
-                                thr = r.x;
-                                minpos = __float_as_int(r.y);
+                            for (int j = 0; j < 32; ++j) {
+                                if (j >= j_start && v[j] > thr) {
+                                    if (cnt < PEND) {
+                                        pend_sc[cnt * BLOCK_M] = v[j];
+                                        pend_id[cnt * BLOCK_M] = idx0 + j;
+                                        ++cnt;
+                                    } else {
+                                        lost_at = min(lost_at, j);
+                                    }
+                                }
                             }
                         }
+                        if (!__any_sync(0xffffffffu, cnt >= PEND)) break;
+                        flush_pending<KP>(my_sc, my_id, pend_sc, pend_id, cnt, thr, minpos);
+                        if (!__any_sync(0xffffffffu, lost_at < 32)) break;
+                        j_start = lost_at;  // re-offer what did not fit (now against the tighter threshold)
                     }
                 }
                 if (++acc == 2) {
@@ -391,6 +491,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     acc_phase ^= 1;
                 }
             }
+            flush_pending<KP>(my_sc, my_id, pend_sc, pend_id, cnt, thr, minpos);
             // write this (query, split) candidate list
             const int q = m_tile * BLOCK_M + row;
             if (q < p.nq) {
@@ -409,12 +510,77 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
     }
 
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+    teardown_ring(ring);
+}
+
+// ---- all-pairs threshold filter (sem_dedup): same mainloop, the epilogue emits (i, j) candidates -------------------
+constexpr int PAIR_STAGES = 4;
+constexpr int PAIR_SMEM = PAIR_STAGES * STAGE_BYTES + 256;
+
+template <bool TF32>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+pair_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x, const FilterParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PAIR_STAGES * STAGE_BYTES);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const Ring ring = setup_ring<PAIR_STAGES>(smem, bars, &tmap_q, &tmap_x);
+    const int n_items = num_items(p);
+    if (warp == 0) {
+        if (lane == 0) producer_loop<TF32, PAIR_STAGES>(&tmap_q, &tmap_x, p, ring);
+    } else if (warp == 1) {
+        if (lane == 0) mma_loop<TF32, PAIR_STAGES>(p, ring);
+    } else if (warp >= EPI_WARP0) {
+        const int quad = warp - EPI_WARP0;
+        const int row = quad * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const float thr = p.pair_thr;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int m_tile, split, t0, t1;
+            item_range(p, item, m_tile, split, t0, t1);
+            const int gi = m_tile * BLOCK_M + row;  // global row of this thread
+            for (int t = t0; t < t1; ++t) {
+                const int col0 = t * BLOCK_N;
+                mbar_wait(&ring.tmem_full[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = ring.tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    float v[32];
+                    tmem_ld32(taddr + c * 32, v);
+                    tmem_ld_wait();
+                    if (c == BLOCK_N / 32 - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&ring.tmem_empty[acc]);
+                    }
+                    float mx = v[0];
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+                    if (mx > thr && gi < p.n) {
+                        const int idx0 = col0 + c * 32;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int gj = idx0 + j;
+                            if (v[j] > thr && gj > gi && gj < p.n) {  // strict upper triangle, inside the matrix
+                                const unsigned long long pos = atomicAdd(p.pair_count, 1ull);
+                                if (pos < p.pair_cap) {
+                                    p.pair_i[pos] = gi;
+                                    p.pair_j[pos] = gj;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
     }
+    teardown_ring(ring);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
@@ -501,7 +667,7 @@ int filter_kp_for_k(int k) {
     if (k <= 6) return 16;
     if (k <= 16) return 32;
     if (k <= 40) return 64;
-    if (k <= 96) return 128;
+    if (k <= 64) return 96;
     return 0;
 }
 
@@ -538,7 +704,7 @@ int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int
         set_error("matrix too large for 32-bit row ids (n=%lld nq=%lld)", (long long)X.n, (long long)nq);
         return B2_ERANGE;
     }
-    const bool tf32 = X.dtype == B2_F32;
+    const bool tf32 = X.filt_dtype == B2_F32;
     const int kb_elems = tf32 ? 32 : 64;
     CUtensorMap tq, tx;
     B2_TRY(make_tmap(&tq, q_filt, tf32, nq, X.d, q_pitch, BLOCK_M));
@@ -555,6 +721,13 @@ int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int
     p.n_ntiles = (int32_t)ceil_div(X.n, BLOCK_N);
     p.tiles_per_split = (int32_t)ceil_div(p.n_ntiles, n_splits);
     p.n_splits = n_splits;
+    p.pair_mode = 0;
+    p.part = 0;
+    p.nparts = 1;
+    p.pair_thr = 0.f;
+    p.pair_i = p.pair_j = nullptr;
+    p.pair_count = nullptr;
+    p.pair_cap = 0;
     if ((int64_t)p.tiles_per_split * (n_splits - 1) >= p.n_ntiles) {
         set_error("internal: empty corpus split (tiles %d, splits %d)", p.n_ntiles, n_splits);
         return B2_EINVAL;
@@ -570,9 +743,57 @@ int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int
         case 16: return launch_kp<16>(is_l2, tf32, tq, tx, p, grid, stream);
         case 32: return launch_kp<32>(is_l2, tf32, tq, tx, p, grid, stream);
         case 64: return launch_kp<64>(is_l2, tf32, tq, tx, p, grid, stream);
-        case 128: return launch_kp<128>(is_l2, tf32, tq, tx, p, grid, stream);
+        case 96: return launch_kp<96>(is_l2, tf32, tq, tx, p, grid, stream);
         default: set_error("internal: unsupported candidate capacity %d", kp); return B2_EINVAL;
     }
+}
+
+// All pairs i < j of X whose filter inner product exceeds thr (sem_dedup). Candidates land in pair_i/pair_j (device,
+// capacity cap) in arbitrary order; *pair_count receives the total found.
+int launch_pair_filter(const MatView& X, float thr, int part, int nparts, int32_t* pair_i, int32_t* pair_j,
+                       unsigned long long* pair_count, unsigned long long cap, int device, cudaStream_t stream) {
+    if (X.n <= 1) return B2_OK;
+    if (X.n > 0x7fffff00LL) {
+        set_error("matrix too large for 32-bit row ids (n=%lld)", (long long)X.n);
+        return B2_ERANGE;
+    }
+    const bool tf32 = X.filt_dtype == B2_F32;
+    const int kb_elems = tf32 ? 32 : 64;
+    CUtensorMap tq, tx;
+    B2_TRY(make_tmap(&tq, X.filt, tf32, X.n, X.d, X.filt_pitch, BLOCK_M));
+    B2_TRY(make_tmap(&tx, X.filt, tf32, X.n, X.d, X.filt_pitch, BLOCK_N));
+    FilterParams p;
+    memset(&p, 0, sizeof(p));
+    p.nq = (int32_t)X.n;
+    p.n = (int32_t)X.n;
+    p.num_kb = (int32_t)ceil_div(X.d, kb_elems);
+    p.n_mtiles = (int32_t)ceil_div(X.n, BLOCK_M);
+    p.n_ntiles = (int32_t)ceil_div(X.n, BLOCK_N);
+    p.n_splits = 1;
+    p.tiles_per_split = p.n_ntiles;
+    p.pair_mode = 1;
+    p.part = part;
+    p.nparts = nparts;
+    p.pair_thr = thr;
+    p.pair_i = pair_i;
+    p.pair_j = pair_j;
+    p.pair_count = pair_count;
+    p.pair_cap = cap;
+    const int64_t items = p.n_mtiles > part ? ceil_div(p.n_mtiles - part, nparts) : 0;
+    if (items <= 0) return B2_OK;
+    const int grid = (int)std::min<int64_t>(items, sm_count(device));
+    if (tf32) {
+        static bool a1 = false;
+        if (!a1) { B2_CUDA(cudaFuncSetAttribute(pair_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM)); a1 = true; }
+        pair_filter_kernel<true><<<grid, NUM_THREADS, PAIR_SMEM, stream>>>(tq, tx, p);
+    } else {
+        static bool a0 = false;
+        if (!a0) { B2_CUDA(cudaFuncSetAttribute(pair_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM)); a0 = true; }
+        pair_filter_kernel<false><<<grid, NUM_THREADS, PAIR_SMEM, stream>>>(tq, tx, p);
+    }
+    B2_LAUNCH_CHECK();
+    g_stats[ST_FILTER_LAUNCHES]++;
+    return B2_OK;
 }
 
 }  // namespace b2

@@ -66,6 +66,9 @@ def lib():
         L.orc_knn.restype = ctypes.c_int
         L.orc_knn.argtypes = [f32p, ctypes.c_int64, ctypes.c_int, f32p, ctypes.c_int64, ctypes.c_int,
                               ctypes.c_int, ctypes.c_int, f32p, i64p]
+        L.orc_knn_blocked.restype = ctypes.c_int
+        L.orc_knn_blocked.argtypes = [f32p, ctypes.c_int64, ctypes.c_int, f32p, ctypes.c_int64, ctypes.c_int,
+                                      ctypes.c_int, f32p, i64p]
         L.orc_threshold_pairs.restype = ctypes.c_int64
         L.orc_threshold_pairs.argtypes = [f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_float, i64p, i64p,
                                           ctypes.c_int64]
@@ -138,6 +141,20 @@ def knn(x, q, k, metric=IP, scorer=CANONICAL):
                        _p(D, ctypes.c_float), _p(I, ctypes.c_int64))
     if rc != 0:
         raise ValueError("orc_knn failed")
+    return D, I
+
+
+def knn_blocked(x, q, k, metric=IP):
+    """Query-blocked fp32 FMA search with the same heap code (faiss BLAS-path analogue): the timed CPU baseline."""
+    x, q = _f32(x), _f32(q)
+    n, d = x.shape
+    nq = q.shape[0]
+    D = np.empty((nq, k), dtype=np.float32)
+    I = np.empty((nq, k), dtype=np.int64)
+    rc = lib().orc_knn_blocked(_p(x, ctypes.c_float), n, d, _p(q, ctypes.c_float), nq, k, metric,
+                               _p(D, ctypes.c_float), _p(I, ctypes.c_int64))
+    if rc != 0:
+        raise ValueError("orc_knn_blocked failed")
     return D, I
 
 

@@ -283,6 +283,79 @@ int orc_knn(const float* x, int64_t n, int d, const float* q, int64_t nq, int k,
     return 0;
 }
 
+/* Blocked variant of orc_knn for the timed CPU baseline: faiss's BLAS path (faiss/utils/distances.cpp
+ * exhaustive_inner_product_blas / exhaustive_L2sqr_blas) multiplies a block of queries with a block of
+ * database rows so that each database row is read once per query block and the FMA pipes stay busy; this
+ * does the same with an ORC_QB-query block per thread and a 4-query x 1-row fp32 FMA micro-kernel.
+ * Rows are still offered to each heap in ascending id. Scores are fp32 with FMA contraction (the precision
+ * class of sgemm); ties and selection follow the same heap code as orc_knn. */
+#define ORC_QB 16
+static inline void dot4_fma(const float* q0, const float* q1, const float* q2, const float* q3, const float* x, int d,
+                            float* out) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma omp simd reduction(+ : a0, a1, a2, a3)
+    for (int i = 0; i < d; ++i) {
+        const float xv = x[i];
+        a0 = __builtin_fmaf(q0[i], xv, a0);
+        a1 = __builtin_fmaf(q1[i], xv, a1);
+        a2 = __builtin_fmaf(q2[i], xv, a2);
+        a3 = __builtin_fmaf(q3[i], xv, a3);
+    }
+    out[0] = a0; out[1] = a1; out[2] = a2; out[3] = a3;
+}
+
+int orc_knn_blocked(const float* x, int64_t n, int d, const float* q, int64_t nq, int k, int metric, float* D,
+                    int64_t* I) {
+    if (k <= 0 || d <= 0) return -1;
+    const int is_max = metric == ORC_L2;
+    float* xn = NULL;
+    if (metric == ORC_L2) {
+        xn = (float*)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+#pragma omp parallel for
+        for (int64_t j = 0; j < n; ++j) xn[j] = dot_f32_fast(x + j * d, x + j * d, d);
+    }
+    const int64_t nblocks = (nq + ORC_QB - 1) / ORC_QB;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t b = 0; b < nblocks; ++b) {
+        const int64_t q0 = b * ORC_QB;
+        const int qb = (int)((nq - q0) < ORC_QB ? (nq - q0) : ORC_QB);
+        float qn[ORC_QB], thresh[ORC_QB], sc[ORC_QB];
+        const float* qp[ORC_QB];
+        for (int t = 0; t < ORC_QB; ++t) qp[t] = q + (q0 + (t < qb ? t : qb - 1)) * d; /* pad the block with its last query */
+        for (int t = 0; t < qb; ++t) {
+            qn[t] = xn ? dot_f32_fast(qp[t], qp[t], d) : 0.f;
+            heap_heapify(is_max, k, D + (q0 + t) * k, I + (q0 + t) * k);
+            thresh[t] = D[(q0 + t) * k];
+        }
+        for (int64_t j = 0; j < n; ++j) {
+            const float* xj = x + j * d;
+            for (int t = 0; t < ORC_QB; t += 4) dot4_fma(qp[t], qp[t + 1], qp[t + 2], qp[t + 3], xj, d, sc + t);
+            for (int t = 0; t < qb; ++t) {
+                float s = sc[t];
+                if (metric == ORC_L2) {
+                    s = qn[t] + xn[j] - 2 * s;
+                    if (s < 0) s = 0;
+                }
+                float* hv = D + (q0 + t) * k;
+                int64_t* hi = I + (q0 + t) * k;
+                if (k == 1) {
+                    if (c_cmp(is_max, hv[0], s)) {
+                        hv[0] = s;
+                        hi[0] = j;
+                    }
+                } else if (c_cmp(is_max, thresh[t], s)) {
+                    heap_replace_top(is_max, k, hv, hi, s, j);
+                    thresh[t] = hv[0];
+                }
+            }
+        }
+        if (k > 1)
+            for (int t = 0; t < qb; ++t) heap_reorder(is_max, k, D + (q0 + t) * k, I + (q0 + t) * k);
+    }
+    free(xn);
+    return 0;
+}
+
 /* all pairs i<j with canonical IP score > thr (strict). Returns the number found; writes up to cap. */
 int64_t orc_threshold_pairs(const float* x, int64_t n, int d, float thr, int64_t* out_i, int64_t* out_j, int64_t cap) {
     int64_t cnt = 0;

@@ -90,7 +90,8 @@ def stage(s):
         ok &= run_case("filter bf16 d100", 3001, 100, 77, 10, 0, "bf16")
         ok &= run_case("filter f32 d30", 2999, 30, 130, 3, 1, "f32")
         ok &= run_case("filter bf16 k1", 4097, 128, 257, 1, 0, "bf16")
-        ok &= run_case("filter bf16 k96", 6000, 128, 100, 96, 0, "bf16")
+        ok &= run_case("filter bf16 k64 (kp96)", 6000, 128, 300, 64, 0, "bf16")
+        ok &= run_case("dense k96", 6000, 128, 100, 96, 0, "bf16")
     elif s == 5:  # tie-heavy data through the filter (forces the certified-fallback path)
         ok &= run_case("filter grid IP", 4096, 32, 64, 10, 0, "f32", grid=True)
         ok &= run_case("filter grid L2", 4096, 32, 64, 10, 1, "bf16", grid=True)

@@ -1,0 +1,205 @@
+"""Host-side mirror of the reference's plugin/operator surface, exercised on CPU with a test-double vector store
+(tests/helpers.NumpyVS, backed by the oracle). The assertions restate what the reference's own operator code does
+(file:line cited per test) and, where the reference has a test for it, mirror that test (.github/tests/rm_tests.py)."""
+import os
+import struct
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import lotus_b200 as lotus
+import oracle
+from helpers import NumpyVS, gauss
+from lotus_b200 import faiss_io
+
+
+@pytest.fixture
+def env(tmp_path):
+    rm = lotus.HashRM(dim=32)
+    vs = NumpyVS()
+    lotus.settings.configure(rm=rm, vs=vs, enable_cache=False)
+    yield rm, vs, tmp_path
+    lotus.settings.configure(rm=None, vs=None)
+
+
+def test_settings_configure_and_context():
+    # lotus/settings.py:41-70
+    with pytest.raises(ValueError, match="Invalid setting"):
+        lotus.settings.configure(nope=1)
+    lotus.settings.configure(enable_cache=False)
+    with lotus.settings.context(enable_cache=True):
+        assert lotus.settings.enable_cache is True
+        with lotus.settings.context(parallel_groupby_max_threads=2):
+            assert lotus.settings.enable_cache is True and lotus.settings.parallel_groupby_max_threads == 2
+    assert lotus.settings.enable_cache is False
+    with pytest.raises(ValueError):
+        with lotus.settings.context(bogus=1):
+            pass
+
+
+def test_rm_passes_ndarrays_through():
+    # lotus/models/rm.py:73-85
+    rm = lotus.HashRM(dim=8)
+    q = np.ones((2, 8), np.float32)
+    assert rm.convert_query_to_query_vector(q) is q
+    assert rm.convert_query_to_query_vector("a").shape == (1, 8)
+    assert rm.convert_query_to_query_vector(pd.Series(["a", "b"])).shape == (2, 8)
+    assert np.array_equal(rm(["x"]), rm(["x"]))
+
+
+def test_faiss_index_file_layout_roundtrip(tmp_path):
+    x = gauss(5, 4, 0)
+    p = str(tmp_path / "index")
+    faiss_io.write_flat_index(p, x, faiss_io.METRIC_INNER_PRODUCT)
+    raw = open(p, "rb").read()
+    # faiss/impl/index_write.cpp: fourcc, d, ntotal, dummy, dummy, is_trained, metric_type, then WRITEXBVECTOR(codes)
+    assert raw[:4] == b"IxFI"
+    d, n, d1, d2, trained, metric = struct.unpack("<iqqqBi", raw[4:4 + 33])
+    assert (d, n, d1, d2, trained, metric) == (4, 5, 1 << 20, 1 << 20, 1, 0)
+    assert struct.unpack("<Q", raw[37:45])[0] == 20 and len(raw) == 45 + 80
+    y, m = faiss_io.read_flat_index(p)
+    assert m == 0 and np.array_equal(x, y)
+    faiss_io.write_flat_index(p, x, faiss_io.METRIC_L2)
+    assert open(p, "rb").read(4) == b"IxF2" and faiss_io.read_flat_index(p)[1] == 1
+    open(p, "wb").write(b"IwFl" + raw[4:])
+    with pytest.raises(ValueError, match="IndexFlat"):
+        faiss_io.read_flat_index(p)
+
+
+def test_index_dir_keeps_the_callers_vecs_like_the_reference(tmp_path):
+    # faiss_vs.py:27-30: vecs is a pickle of the array as given (float64 for LiteLLMRM), the index holds float32
+    x64 = gauss(6, 8, 1).astype(np.float64)
+    faiss_io.write_index_dir(str(tmp_path / "d"), x64, x64.astype(np.float32), 0)
+    vecs, x, metric = faiss_io.read_index_dir(str(tmp_path / "d"))
+    assert vecs.dtype == np.float64 and x.dtype == np.float32 and np.array_equal(vecs.astype(np.float32), x)
+    with pytest.raises(ValueError, match="not found"):
+        faiss_io.read_index_dir(str(tmp_path / "missing"))
+
+
+def test_sem_index_sets_attrs_and_load_sem_index(env):
+    rm, vs, tmp = env
+    df = pd.DataFrame({"t": ["a", "b", "c"]})
+    out = df.sem_index("t", str(tmp / "i1"))
+    assert out is df and df.attrs["index_dirs"]["t"] == str(tmp / "i1") and vs.index_dir == str(tmp / "i1")
+    df["u"] = ["x", "y", "z"]
+    df.sem_index("u", str(tmp / "i2"))
+    assert set(df.attrs["index_dirs"]) == {"t", "u"}  # pandas>=3 accessor re-creation must not wipe earlier entries
+    df2 = pd.DataFrame({"t": ["a", "b", "c"]}).load_sem_index("t", str(tmp / "i1"))
+    assert df2.attrs["index_dirs"] == {"t": str(tmp / "i1")}
+    with pytest.raises(AttributeError):
+        pd.Series([1]).to_frame().T.sem_index  # accessor only validates DataFrames; a frame is fine
+        lotus.sem_ops.SemIndexDataframe([1, 2])
+
+
+def reference_sim_join(left, right, vs, rm, left_on, right_on, K, lsuffix="", rsuffix="", score_suffix="", keep_index=False):
+    """lotus/sem_ops/sem_sim_join.py:130-166 restated literally (Python double loop + the two joins)."""
+    queries = left[left_on]
+    qv = rm.convert_query_to_query_vector(queries)
+    out = vs(qv, K, ids=list(right.index))
+    other_index_set = set(right.index)
+    join_results = []
+    for q_idx, res_ids in enumerate(out.indices):
+        for i, res_id in enumerate(res_ids):
+            if res_id != -1 and res_id in other_index_set:
+                join_results.append((left.index[q_idx], res_id, out.distances[q_idx][i]))
+    df1, df2 = left.copy(), right.copy()
+    df1["_left_id"] = df1.index
+    df2["_right_id"] = df2.index
+    temp_df = pd.DataFrame(join_results, columns=["_left_id", "_right_id", "_scores" + score_suffix])
+    joined = df1.join(temp_df.set_index("_left_id"), how="right", on="_left_id").join(
+        df2.set_index("_right_id"), how="left", on="_right_id", lsuffix=lsuffix, rsuffix=rsuffix)
+    if not keep_index:
+        joined.drop(columns=["_left_id", "_right_id"], inplace=True)
+    return joined
+
+
+@pytest.mark.parametrize("keep_index", [False, True])
+def test_sem_sim_join_equals_the_reference_control_flow(env, keep_index):
+    rm, vs, tmp = env
+    left = pd.DataFrame({"a": [f"l{i}" for i in range(7)], "v": range(7)})
+    right = pd.DataFrame({"b": [f"r{i}" for i in range(11)], "v": range(11)}).sem_index("b", str(tmp / "r"))
+    got = left.sem_sim_join(right, "a", "b", K=3, lsuffix="_l", rsuffix="_r", keep_index=keep_index)
+    want = reference_sim_join(left, right, vs, rm, "a", "b", 3, "_l", "_r", keep_index=keep_index)
+    assert list(got.columns) == list(want.columns) and len(got) == 21
+    pd.testing.assert_frame_equal(got.reset_index(drop=True), want.reset_index(drop=True), check_dtype=False)
+    assert list(got.index) == list(want.index)
+    # filtered right frame: only its rows may come back (ids=list(other.index), sem_sim_join.py:132-134)
+    sub = right[right["v"] % 2 == 0]
+    got = left.sem_sim_join(sub, "a", "b", K=4, lsuffix="_l", rsuffix="_r")
+    assert set(got["b"]) <= set(sub["b"]) and len(got) == 28
+    # K larger than the right frame: every right row once per left row, -1 padding dropped
+    got = left.sem_sim_join(sub, "a", "b", K=50, lsuffix="_l", rsuffix="_r")
+    assert len(got) == 7 * len(sub)
+
+
+def test_sem_sim_join_errors_like_the_reference(env):
+    rm, vs, tmp = env
+    left = pd.DataFrame({"a": ["x"]})
+    right = pd.DataFrame({"b": ["y"]})
+    with pytest.raises(ValueError, match="Index directory for column b not found"):
+        left.sem_sim_join(right, "a", "b", K=1)
+    with pytest.raises(ValueError, match="must have a name"):
+        left.sem_sim_join(pd.Series(["y"]), "a", "b", K=1)
+    lotus.settings.configure(vs=None)
+    with pytest.raises(ValueError, match="retrieval model"):
+        left.sem_sim_join(right, "a", "b", K=1)
+
+
+def test_sem_sim_join_reference_test_case(env):
+    # .github/tests/rm_tests.py:103-123 (test_sim_join) with table embeddings standing in for the live model
+    rm, vs, tmp = env
+    e = {"History of the Atlantic World": [1, 0.1, 0], "Riemannian Geometry": [0, 0.2, 1], "Math": [0, 0, 1], "History": [1, 0, 0]}
+    lotus.settings.configure(rm=lotus.TableRM({k: np.asarray(v, np.float32) for k, v in e.items()}))
+    df1 = pd.DataFrame({"Course Name": ["History of the Atlantic World", "Riemannian Geometry"]})
+    df2 = pd.DataFrame({"Skill": ["Math", "History"]}).sem_index("Skill", str(tmp / "s"))
+    joined = df1.sem_sim_join(df2, left_on="Course Name", right_on="Skill", K=1)
+    assert set(zip(joined["Course Name"], joined["Skill"])) == {("History of the Atlantic World", "History"), ("Riemannian Geometry", "Math")}
+
+
+def test_sem_search_topk_scores_and_filtered_frames(env):
+    rm, vs, tmp = env
+    df = pd.DataFrame({"t": [f"doc{i}" for i in range(20)]}).sem_index("t", str(tmp / "s"))
+    q = "doc7"
+    out = df.sem_search("t", q, K=4, return_scores=True)
+    D, I = oracle.knn(rm(df["t"].tolist()), rm([q]), 4)
+    assert list(out.index) == I[0].tolist() and np.allclose(out["vec_scores_sim_score"], D[0])
+    assert out.attrs["index_dirs"] == df.attrs["index_dirs"] and out["t"].iloc[0] == "doc7"
+    # filtered frame (sem_search.py:116-138 K-doubling loop in the reference): same rows, one search
+    sub = df[df.index % 3 == 0]
+    out = sub.sem_search("t", q, K=5, return_scores=True)
+    ids = np.asarray(sub.index)
+    Ds, Is = oracle.knn_subset(rm(df["t"].tolist()), rm([q]), 5, ids)
+    assert list(out.index) == Is[0].tolist() and np.allclose(out["vec_scores_sim_score"], Ds[0])
+    assert len(df.sem_search("t", q, K=100)) == 20  # K = min(K, len(df)) (sem_search.py:118)
+    assert len(df.iloc[0:0].sem_search("t", q, K=3)) == 0
+    with pytest.raises(AssertionError):
+        df.sem_search("t", q)
+    with pytest.raises(ValueError, match="Reranker not found"):
+        df.sem_search("t", q, K=2, n_rerank=1)
+
+
+def test_cluster_fn_validation(env):
+    # lotus/utils.py:35-39,49-52
+    from lotus_b200.utils import cluster
+    df = pd.DataFrame({"t": ["a", "b"]})
+    with pytest.raises(ValueError, match="Column zz not found"):
+        cluster("zz", 1)(df)
+    with pytest.raises(ValueError, match="Number of centroids must be less than number of documents. 5 > 2"):
+        cluster("t", 5)(df)
+    with pytest.raises(ValueError, match="Index directory for column t not found"):
+        cluster("t", 1)(df)
+
+
+def test_partition_by_stores_ids(env):
+    df = pd.DataFrame({"t": ["a", "b", "c"]})
+    out = df.sem_partition_by(lambda d: [2, 0, 2])
+    assert out is df and df["_lotus_partition_id"].tolist() == [2, 0, 2]
+
+
+def test_operator_cache_passthrough_and_reference_failure_mode(env):
+    rm, vs, tmp = env
+    df = pd.DataFrame({"t": ["a", "b"]})
+    with lotus.settings.context(enable_cache=True):  # lotus/cache.py:38-41: dereferences settings.lm.cache
+        with pytest.raises(AttributeError):
+            df.sem_index("t", str(tmp / "c"))
