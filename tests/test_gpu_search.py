@@ -68,11 +68,16 @@ def test_filter_path_dims(gpu, dtype, d):
 
 
 @pytest.mark.parametrize("metric", [0, 1])
-def test_filter_path_tie_heavy_grid_takes_certified_fallback(gpu, metric):
-    """Massive exact ties around rank k: the certificate cannot hold, the dense exact path must take over and
-    reproduce faiss's heap rule."""
-    st = check(gpu, grid(5000, 8, 6), grid(64, 8, 7), 10, metric, "f32", expect_filter=True)
+def test_filter_path_tie_heavy_takes_certified_fallback(gpu, metric):
+    """Thousands of rows share each score level (coordinates in {-1/2, 0, 1/2}, d = 4: nine possible values), so the
+    K-th and the KP-th best scores coincide: the certificate cannot hold, the dense exact path must take over and
+    reproduce faiss's heap rule (which rows of the tied level survive, and in which order)."""
+    rng = np.random.default_rng(6)
+    x = (rng.integers(-1, 2, size=(5000, 4)) / 2).astype(np.float32)
+    q = (rng.integers(-1, 2, size=(64, 4)) / 2).astype(np.float32)
+    st = check(gpu, x, q, 10, metric, "f32", expect_filter=True)
     assert st["fallback_queries"] > 0
+    check(gpu, grid(5000, 8, 6), grid(64, 8, 7), 10, metric, "bf16", expect_filter=True)
 
 
 def test_unnormalised_and_duplicate_rows(gpu):
