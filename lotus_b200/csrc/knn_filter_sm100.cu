@@ -66,10 +66,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(20000u)  // suspend-time hint (ns): sleep in hardware instead of spinning
             : "memory");
         if (done) break;
         if ((++spins & 0x3ffu) == 0) {
@@ -347,10 +347,10 @@ __device__ __forceinline__ void list_insert(float* sc, int32_t* id, float s, int
 
 // Merge every lane's pending candidates into its list. Warp-collective: the loop bound is the warp-wide
 // maximum so the 32 lanes (32 different queries) execute their insertions together instead of one lane at a
-// time (the divergent version of this cost ~20x more issue slots).
+// time (the divergent version of this cost ~20x more issue slots). Returns (new threshold, position of the minimum).
 template <int KP>
-__device__ __forceinline__ void flush_pending(float* my_sc, int32_t* my_id, const float* pend_sc, const int32_t* pend_id,
-                                              int& cnt, float& thr, int& minpos) {
+__device__ __noinline__ float2 flush_pending(float* my_sc, int32_t* my_id, const float* pend_sc, const int32_t* pend_id,
+                                             int cnt, float thr, int minpos) {
     int mx = cnt;
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
@@ -361,7 +361,7 @@ __device__ __forceinline__ void flush_pending(float* my_sc, int32_t* my_id, cons
         }
         __syncwarp();
     }
-    cnt = 0;
+    return make_float2(thr, __int_as_float(minpos));
 }
 
 template <int KP, bool IS_L2, bool TF32>
@@ -458,32 +458,48 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                         for (int j = 0; j < 32; ++j)
                             if (j >= valid) v[j] = -INFINITY;
                     }
-                    float mx = v[0];
+                    // gate in two levels: the whole 32x32 block, then 8-column groups. Only groups in which some row
+                    // has a score above its threshold run the (long) predicated append code.
+                    float gm[4];
 #pragma unroll
-                    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
-                    if (!__any_sync(0xffffffffu, mx > thr)) continue;  // nothing in this 32x32 block beats any row's threshold
+                    for (int g = 0; g < 4; ++g) {
+                        float m = v[8 * g];
+#pragma unroll
+                        for (int jj = 1; jj < 8; ++jj) m = fmaxf(m, v[8 * g + jj]);
+                        gm[g] = m;
+                    }
+                    const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+                    if (!__any_sync(0xffffffffu, mx > thr)) continue;
                     const int idx0 = col0 + c * 32;
-                    int j_start = 0;
-                    while (true) {  // warp-uniform loop; a second trip only after a buffer overflowed mid-chunk
-                        int lost_at = 32;
-                        if (mx > thr) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                if (j >= j_start && v[j] > thr) {
-                                    if (cnt < PEND) {
-                                        pend_sc[cnt * BLOCK_M] = v[j];
-                                        pend_id[cnt * BLOCK_M] = idx0 + j;
-                                        ++cnt;
-                                    } else {
-                                        lost_at = min(lost_at, j);
+                    for (int g = 0; g < 4; ++g) {
+                        if (!__any_sync(0xffffffffu, gm[g] > thr)) continue;
+                        int j_start = 8 * g;
+                        while (true) {  // warp-uniform loop; a second trip only after a buffer overflowed mid-group
+                            int lost_at = 32;
+                            if (gm[g] > thr) {
+#pragma unroll
+                                for (int jj = 0; jj < 8; ++jj) {
+                                    const int j = 8 * g + jj;
+                                    if (j >= j_start && v[j] > thr) {
+                                        if (cnt < PEND) {
+                                            pend_sc[cnt * BLOCK_M] = v[j];
+                                            pend_id[cnt * BLOCK_M] = idx0 + j;
+                                            ++cnt;
+                                        } else {
+                                            lost_at = min(lost_at, j);
+                                        }
                                     }
                                 }
                             }
+                            if (!__any_sync(0xffffffffu, cnt >= PEND)) break;
+                            const float2 fr = flush_pending<KP>(my_sc, my_id, pend_sc, pend_id, cnt, thr, minpos);
+                            thr = fr.x;
+                            minpos = __float_as_int(fr.y);
+                            cnt = 0;
+                            if (!__any_sync(0xffffffffu, lost_at < 32)) break;
+                            j_start = lost_at;  // re-offer what did not fit (now against the tighter threshold)
                         }
-                        if (!__any_sync(0xffffffffu, cnt >= PEND)) break;
-                        flush_pending<KP>(my_sc, my_id, pend_sc, pend_id, cnt, thr, minpos);
-                        if (!__any_sync(0xffffffffu, lost_at < 32)) break;
-                        j_start = lost_at;  // re-offer what did not fit (now against the tighter threshold)
                     }
                 }
                 if (++acc == 2) {
@@ -491,7 +507,12 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     acc_phase ^= 1;
                 }
             }
-            flush_pending<KP>(my_sc, my_id, pend_sc, pend_id, cnt, thr, minpos);
+            {
+                const float2 fr = flush_pending<KP>(my_sc, my_id, pend_sc, pend_id, cnt, thr, minpos);
+                thr = fr.x;
+                minpos = __float_as_int(fr.y);
+                cnt = 0;
+            }
             // write this (query, split) candidate list
             const int q = m_tile * BLOCK_M + row;
             if (q < p.nq) {
