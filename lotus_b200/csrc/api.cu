@@ -120,7 +120,8 @@ int search_core(b2_index* idx, const MatView& X, int metric, const void* q_dev, 
         const char* qc = reinterpret_cast<const char*>(q_dev) + (size_t)q0 * X.d * esize(q_dtype);
         float* osc = out_sc + (size_t)q0 * k;
         int64_t* oid = out_id + (size_t)q0 * k;
-        const int n_splits = filter_choose_splits(nqc, X.n, dev_sms);
+        const bool two_cta = filter_use_pair(nqc);
+        const int n_splits = filter_choose_splits(nqc, X.n, dev_sms, two_cta);
         if (!q_in_place) B2_TRY(idx->q_filt.ensure((size_t)nqc * q_pitch * esize(filt_dtype)));
         const void* q_filt = q_in_place ? static_cast<const void*>(qc) : idx->q_filt.p;
         B2_TRY(idx->cand_score.ensure((size_t)nqc * n_splits * kp * sizeof(float)));
@@ -130,7 +131,7 @@ int search_core(b2_index* idx, const MatView& X, int metric, const void* q_dev, 
         B2_TRY(idx->h_flags.ensure((size_t)nqc * sizeof(int32_t)));
         if (!q_in_place) B2_TRY(launch_prep_queries(qc, q_dtype, nqc, X.d, idx->q_filt.p, filt_dtype, q_pitch, st));
         B2_CUDA(cudaEventRecord(idx->ev0, st));
-        B2_TRY(launch_knn_filter(X, q_filt, q_pitch, nqc, metric, kp, n_splits, idx->cand_score.as<float>(),
+        B2_TRY(launch_knn_filter(X, q_filt, q_pitch, nqc, metric, kp, n_splits, two_cta, idx->cand_score.as<float>(),
                                  idx->cand_id.as<int32_t>(), idx->cand_thr.as<float>(), idx->device, st));
         B2_CUDA(cudaEventRecord(idx->ev1, st));
         B2_TRY(launch_finalize(X, qc, q_dtype, nqc, metric, k, kp, n_splits, idx->cand_score.as<float>(),

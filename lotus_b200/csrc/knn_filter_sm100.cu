@@ -39,11 +39,16 @@ constexpr int SMEM_LIMIT = 232448;  // 227 KB
 constexpr int PEND = 16;  // pending (not yet merged) candidates per query row between lockstep flushes
 __host__ __device__ constexpr int list_bytes(int kp) { return (kp + PEND) * BLOCK_M * 8; }
 __host__ __device__ constexpr int misc_bytes() { return 2 * BLOCK_N * 4 /*xnorm*/ + 256 /*barriers*/; }
-__host__ __device__ constexpr int num_stages(int kp) {
-    int s = (SMEM_LIMIT - list_bytes(kp) - misc_bytes()) / STAGE_BYTES;
+// cta_group::2 (a CTA pair computes 256 queries x 256 corpus rows): each CTA stages its own 128 query rows and HALF of
+// the corpus tile, so a stage is 32 KB instead of 48 KB and the corpus bytes per SM drop by half.
+__host__ __device__ constexpr int stage_bytes(bool two) { return two ? STAGE_A_BYTES + STAGE_B_BYTES / 2 : STAGE_BYTES; }
+__host__ __device__ constexpr int num_stages(int kp, bool two = false) {
+    int s = (SMEM_LIMIT - list_bytes(kp) - misc_bytes()) / stage_bytes(two);
     return s > 6 ? 6 : s;
 }
-__host__ __device__ constexpr int smem_bytes(int kp) { return num_stages(kp) * STAGE_BYTES + list_bytes(kp) + misc_bytes(); }
+__host__ __device__ constexpr int smem_bytes(int kp, bool two = false) {
+    return num_stages(kp, two) * stage_bytes(two) + list_bytes(kp) + misc_bytes();
+}
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -142,6 +147,61 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) variants ------------------------------------------------------------------------
+// In a 2-CTA cluster bit 24 of a shared::cluster address selects the CTA of the pair; clearing it addresses the
+// same offset in the leader (even) CTA.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+// executed by BOTH CTAs: the data lands in the issuing CTA's smem, the transaction bytes are counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrive (once the pair's MMAs retire) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (TF32) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+
 // UMMA shared-memory descriptor: K-major operand tile, rows of 128 bytes, SWIZZLE_128B (the layout a
 // TMA box {128 B, rows} with CU_TENSOR_MAP_SWIZZLE_128B lands in). 8-row groups are 1024 B apart (SBO).
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
@@ -154,10 +214,10 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
     return desc;
 }
 // UMMA instruction descriptor: D fp32, A/B bf16 (1) or tf32 (2), both K-major, M = 128, N = 256.
-template <bool TF32>
+template <bool TF32, int M = BLOCK_M>
 __device__ __forceinline__ constexpr uint32_t make_idesc() {
     const uint32_t fmt = TF32 ? 2u : 1u;
-    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 struct FilterParams {
@@ -169,6 +229,7 @@ struct FilterParams {
     int32_t n;
     int32_t num_kb;        // K-blocks per tile = ceil(d / elements per 128 B)
     int32_t n_mtiles;      // ceil(nq / 128)
+    int32_t n_munits;      // schedulable query units: n_mtiles, or ceil(n_mtiles / 2) CTA pairs in cta_group::2 mode
     int32_t n_splits;
     int32_t tiles_per_split;  // corpus tiles (of 256 rows) per split
     int32_t n_ntiles;         // ceil(n / 256)
@@ -188,43 +249,73 @@ struct Ring {
     uint32_t tmem_base;
 };
 
+// Persistent schedule. A "worker" is a CTA (or a CTA pair); item = (query unit, corpus split), unit fastest so that
+// co-resident workers stream the same corpus tiles and share them in L2.
+struct Sched {
+    int worker, n_workers, rank;  // rank = CTA rank inside the pair (0 in single-CTA mode)
+};
+template <bool TWO>
+__device__ __forceinline__ Sched make_sched() {
+    Sched sc;
+    if constexpr (TWO) {
+        sc.worker = blockIdx.x >> 1;
+        sc.n_workers = gridDim.x >> 1;
+        sc.rank = (int)cluster_ctarank();
+    } else {
+        sc.worker = blockIdx.x;
+        sc.n_workers = gridDim.x;
+        sc.rank = 0;
+    }
+    return sc;
+}
 __device__ __forceinline__ int num_items(const FilterParams& p) {
     if (p.pair_mode) return p.n_mtiles > p.part ? (p.n_mtiles - p.part + p.nparts - 1) / p.nparts : 0;
-    return p.n_mtiles * p.n_splits;
+    return p.n_munits * p.n_splits;
 }
-__device__ __forceinline__ void item_range(const FilterParams& p, int item, int& m_tile, int& split, int& t0, int& t1) {
+template <bool TWO>
+__device__ __forceinline__ void item_range(const FilterParams& p, const Sched& sc, int item, int& m_tile, int& split, int& t0,
+                                           int& t1) {
     if (p.pair_mode) {
         m_tile = p.part + item * p.nparts;
         split = 0;
         t0 = (m_tile * BLOCK_M) / BLOCK_N;  // first corpus tile that can contain a column > row
         t1 = p.n_ntiles;
     } else {
-        m_tile = item % p.n_mtiles;
-        split = item / p.n_mtiles;
+        const int unit = item % p.n_munits;
+        m_tile = TWO ? 2 * unit + sc.rank : unit;
+        split = item / p.n_munits;
         t0 = split * p.tiles_per_split;
         t1 = min(t0 + p.tiles_per_split, p.n_ntiles);
     }
 }
 
-// TMA producer: one elected lane streams (query tile, corpus tile) K-blocks into the smem ring.
-template <bool TF32, int NSTAGES>
+// TMA producer: one elected lane (per CTA) streams (query tile, corpus tile) K-blocks into the smem ring.
+template <bool TF32, int NSTAGES, bool TWO>
 __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap_q, const CUtensorMap* tmap_x, const FilterParams& p,
-                                              const Ring& r) {
+                                              const Ring& r, const Sched& sc) {
     constexpr int KB_ELEMS = TF32 ? 32 : 64;  // elements per 128-byte K-block row
+    constexpr int SB = stage_bytes(TWO);
     const int n_items = num_items(p);
     int stage = 0;
     uint32_t phase = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int item = sc.worker; item < n_items; item += sc.n_workers) {
         int m_tile, split, t0, t1;
-        item_range(p, item, m_tile, split, t0, t1);
+        item_range<TWO>(p, sc, item, m_tile, split, t0, t1);
         for (int t = t0; t < t1; ++t) {
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 mbar_wait(&r.empty_bar[stage], phase ^ 1);
-                uint8_t* sa = r.stage_base + stage * STAGE_BYTES;
+                uint8_t* sa = r.stage_base + stage * SB;
                 uint8_t* sb = sa + STAGE_A_BYTES;
-                mbar_arrive_expect_tx(&r.full_bar[stage], STAGE_BYTES);
-                tma_load_2d(sa, tmap_q, &r.full_bar[stage], kb * KB_ELEMS, m_tile * BLOCK_M);
-                tma_load_2d(sb, tmap_x, &r.full_bar[stage], kb * KB_ELEMS, t * BLOCK_N);
+                if constexpr (TWO) {
+                    // the leader's full barrier counts the bytes of BOTH CTAs (2 x 32 KB); only the leader arms it
+                    if (sc.rank == 0) mbar_arrive_expect_tx(&r.full_bar[stage], 2 * SB);
+                    tma_load_2d_pair(sa, tmap_q, &r.full_bar[stage], kb * KB_ELEMS, m_tile * BLOCK_M);
+                    tma_load_2d_pair(sb, tmap_x, &r.full_bar[stage], kb * KB_ELEMS, t * BLOCK_N + sc.rank * (BLOCK_N / 2));
+                } else {
+                    mbar_arrive_expect_tx(&r.full_bar[stage], SB);
+                    tma_load_2d(sa, tmap_q, &r.full_bar[stage], kb * KB_ELEMS, m_tile * BLOCK_M);
+                    tma_load_2d(sb, tmap_x, &r.full_bar[stage], kb * KB_ELEMS, t * BLOCK_N);
+                }
                 if (++stage == NSTAGES) {
                     stage = 0;
                     phase ^= 1;
@@ -234,18 +325,20 @@ __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap_q, const C
     }
 }
 
-// MMA issuer: one elected lane issues tcgen05.mma for every K-block, accumulating a 128x256 fp32 tile in TMEM.
-template <bool TF32, int NSTAGES>
-__device__ __forceinline__ void mma_loop(const FilterParams& p, const Ring& r) {
-    constexpr uint32_t idesc = make_idesc<TF32>();
+// MMA issuer: one elected lane (of the leader CTA in pair mode) issues tcgen05.mma for every K-block, accumulating a
+// 128x256 fp32 tile per CTA in TMEM.
+template <bool TF32, int NSTAGES, bool TWO>
+__device__ __forceinline__ void mma_loop(const FilterParams& p, const Ring& r, const Sched& sc) {
+    constexpr uint32_t idesc = make_idesc<TF32, TWO ? 2 * BLOCK_M : BLOCK_M>();
+    constexpr int SB = stage_bytes(TWO);
     const int n_items = num_items(p);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int item = sc.worker; item < n_items; item += sc.n_workers) {
         int m_tile, split, t0, t1;
-        item_range(p, item, m_tile, split, t0, t1);
+        item_range<TWO>(p, sc, item, m_tile, split, t0, t1);
         for (int t = t0; t < t1; ++t) {
             mbar_wait(&r.tmem_empty[acc], acc_phase ^ 1);
             tc_fence_after();
@@ -253,21 +346,28 @@ __device__ __forceinline__ void mma_loop(const FilterParams& p, const Ring& r) {
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 mbar_wait(&r.full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(r.stage_base + stage * STAGE_BYTES);
+                const uint32_t sa = smem_u32(r.stage_base + stage * SB);
                 const uint64_t adesc = make_sw128_desc(sa);
                 const uint64_t bdesc = make_sw128_desc(sa + STAGE_A_BYTES);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     // +32 bytes per UMMA_K step inside the 128-byte swizzle row (start address is in 16 B units)
-                    tc_mma<TF32>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    if constexpr (TWO)
+                        tc_mma_pair<TF32>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    else
+                        tc_mma<TF32>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
                 }
-                tc_commit(&r.empty_bar[stage]);  // frees the smem stage when these MMAs retire
+                // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+                if constexpr (TWO) tc_commit_pair(&r.empty_bar[stage]);
+                else tc_commit(&r.empty_bar[stage]);
                 if (++stage == NSTAGES) {
                     stage = 0;
                     phase ^= 1;
                 }
             }
-            tc_commit(&r.tmem_full[acc]);  // accumulator complete -> epilogue
+            // accumulator complete -> epilogue (of both CTAs)
+            if constexpr (TWO) tc_commit_pair(&r.tmem_full[acc]);
+            else tc_commit(&r.tmem_full[acc]);
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;
@@ -276,8 +376,8 @@ __device__ __forceinline__ void mma_loop(const FilterParams& p, const Ring& r) {
     }
 }
 
-// barrier init + TMEM allocation shared by both kernels; returns after the block-wide sync
-template <int NSTAGES>
+// barrier init + TMEM allocation shared by both kernels; returns after the block-wide (cluster-wide) sync
+template <int NSTAGES, bool TWO>
 __device__ __forceinline__ Ring setup_ring(uint8_t* smem, uint64_t* bars, const CUtensorMap* tmap_q, const CUtensorMap* tmap_x) {
     Ring r;
     r.stage_base = smem;
@@ -298,29 +398,36 @@ __device__ __forceinline__ Ring setup_ring(uint8_t* smem, uint64_t* bars, const 
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < NSTAGES; ++s) {
-            mbar_init(&r.full_bar[s], 1);
-            mbar_init(&r.empty_bar[s], 1);
+            mbar_init(&r.full_bar[s], 1);   // the (leader's) producer arms it; TMA completes the bytes
+            mbar_init(&r.empty_bar[s], 1);  // one tcgen05.commit arrival (multicast to both CTAs in pair mode)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&r.tmem_full[a], 1);
-            mbar_init(&r.tmem_empty[a], 4);  // one arrive per epilogue warp
+            mbar_init(&r.tmem_empty[a], TWO ? 8 : 4);  // one arrive per epilogue warp (of both CTAs, on the leader)
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_ptr, TMEM_COLS);
+    if (warp == 2) {
+        if constexpr (TWO) tmem_alloc_pair(tmem_ptr, TMEM_COLS);
+        else tmem_alloc(tmem_ptr, TMEM_COLS);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (TWO) cluster_sync_all();  // peers must see initialised barriers before any remote arrive / TMA
+    else __syncthreads();
     tc_fence_after();
     r.tmem_base = *tmem_ptr;
     return r;
 }
 
+template <bool TWO>
 __device__ __forceinline__ void teardown_ring(const Ring& r) {
     tc_fence_before();
-    __syncthreads();
+    if constexpr (TWO) cluster_sync_all();  // nobody leaves while the peer may still touch its smem / TMEM / barriers
+    else __syncthreads();
     if ((threadIdx.x >> 5) == 2) {
         tc_fence_after();
-        tmem_dealloc(r.tmem_base, TMEM_COLS);
+        if constexpr (TWO) tmem_dealloc_pair(r.tmem_base, TMEM_COLS);
+        else tmem_dealloc(r.tmem_base, TMEM_COLS);
     }
 }
 
@@ -364,17 +471,15 @@ __device__ __noinline__ float2 flush_pending(float* my_sc, int32_t* my_id, const
     return make_float2(thr, __int_as_float(minpos));
 }
 
-template <int KP, bool IS_L2, bool TF32>
+template <int KP, bool IS_L2, bool TF32, bool TWO>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
                   const FilterParams p) {
-    constexpr int NSTAGES = num_stages(KP);
+    constexpr int NSTAGES = num_stages(KP, TWO);
     static_assert(NSTAGES >= 2, "not enough shared memory for the operand ring");
-    constexpr int KB_ELEMS = TF32 ? 32 : 64;  // elements per 128-byte K-block row
 
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* stage_base = smem;
-    float* list_sc = reinterpret_cast<float*>(smem + NSTAGES * STAGE_BYTES);
+    float* list_sc = reinterpret_cast<float*>(smem + NSTAGES * stage_bytes(TWO));
     int32_t* list_id = reinterpret_cast<int32_t*>(list_sc + KP * BLOCK_M);
     float* pend_sc_base = reinterpret_cast<float*>(list_id + KP * BLOCK_M);     // [PEND][BLOCK_M]
     int32_t* pend_id_base = reinterpret_cast<int32_t*>(pend_sc_base + PEND * BLOCK_M);
@@ -382,16 +487,17 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_xn + 2 * BLOCK_N);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const Ring ring = setup_ring<NSTAGES>(smem, bars, &tmap_q, &tmap_x);
+    const Ring ring = setup_ring<NSTAGES, TWO>(smem, bars, &tmap_q, &tmap_x);
     uint64_t* tmem_full = ring.tmem_full;
     uint64_t* tmem_empty = ring.tmem_empty;
     const uint32_t tmem_base = ring.tmem_base;
     const int n_items = num_items(p);
+    const Sched sc = make_sched<TWO>();
 
     if (warp == 0) {
-        if (lane == 0) producer_loop<TF32, NSTAGES>(&tmap_q, &tmap_x, p, ring);
+        if (lane == 0) producer_loop<TF32, NSTAGES, TWO>(&tmap_q, &tmap_x, p, ring, sc);
     } else if (warp == 1) {
-        if (lane == 0) mma_loop<TF32, NSTAGES>(p, ring);
+        if (lane == 0 && sc.rank == 0) mma_loop<TF32, NSTAGES, TWO>(p, ring, sc);
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue: streaming top-KP per query row =====================
         const int quad = warp - EPI_WARP0;   // == warp % 4: the TMEM lane quarter this warp may read
@@ -403,9 +509,9 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         int32_t* pend_id = pend_id_base + row;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int item = sc.worker; item < n_items; item += sc.n_workers) {
             int m_tile, split, t0, t1;
-            item_range(p, item, m_tile, split, t0, t1);
+            item_range<TWO>(p, sc, item, m_tile, split, t0, t1);
 #pragma unroll 4
             for (int i = 0; i < KP; ++i) {
                 my_sc[i * BLOCK_M] = -INFINITY;
@@ -435,10 +541,13 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     tmem_ld32(taddr + c * 32, v);
                     tmem_ld_wait();
                     if (c == BLOCK_N / 32 - 1) {
-                        // whole accumulator stage now in registers: hand TMEM back to the MMA warp
+                        // whole accumulator stage now in registers: hand TMEM back to the (leader's) MMA warp
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                        if (lane == 0) {
+                            if constexpr (TWO) mbar_arrive_leader(&tmem_empty[acc]);
+                            else mbar_arrive(&tmem_empty[acc]);
+                        }
                     }
                     if constexpr (IS_L2) {
                         const float4* xn4 = reinterpret_cast<const float4*>(s_xn + acc * BLOCK_N + c * 32);
@@ -531,7 +640,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
     }
 
-    teardown_ring(ring);
+    teardown_ring<TWO>(ring);
 }
 
 // ---- all-pairs threshold filter (sem_dedup): same mainloop, the epilogue emits (i, j) candidates -------------------
@@ -545,21 +654,22 @@ pair_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PAIR_STAGES * STAGE_BYTES);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const Ring ring = setup_ring<PAIR_STAGES>(smem, bars, &tmap_q, &tmap_x);
+    const Ring ring = setup_ring<PAIR_STAGES, false>(smem, bars, &tmap_q, &tmap_x);
     const int n_items = num_items(p);
+    const Sched sc = make_sched<false>();
     if (warp == 0) {
-        if (lane == 0) producer_loop<TF32, PAIR_STAGES>(&tmap_q, &tmap_x, p, ring);
+        if (lane == 0) producer_loop<TF32, PAIR_STAGES, false>(&tmap_q, &tmap_x, p, ring, sc);
     } else if (warp == 1) {
-        if (lane == 0) mma_loop<TF32, PAIR_STAGES>(p, ring);
+        if (lane == 0) mma_loop<TF32, PAIR_STAGES, false>(p, ring, sc);
     } else if (warp >= EPI_WARP0) {
         const int quad = warp - EPI_WARP0;
         const int row = quad * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
         const float thr = p.pair_thr;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int item = sc.worker; item < n_items; item += sc.n_workers) {
             int m_tile, split, t0, t1;
-            item_range(p, item, m_tile, split, t0, t1);
+            item_range<false>(p, sc, item, m_tile, split, t0, t1);
             const int gi = m_tile * BLOCK_M + row;  // global row of this thread
             for (int t = t0; t < t1; ++t) {
                 const int col0 = t * BLOCK_N;
@@ -601,7 +711,7 @@ pair_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             }
         }
     }
-    teardown_ring(ring);
+    teardown_ring<false>(ring);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
@@ -647,30 +757,54 @@ int make_tmap(CUtensorMap* map, const void* base, bool tf32, int64_t rows, int64
     return B2_OK;
 }
 
-template <int KP, bool IS_L2, bool TF32>
+template <int KP, bool IS_L2, bool TF32, bool TWO>
 int launch_variant(const CUtensorMap& tq, const CUtensorMap& tx, const FilterParams& p, int grid, cudaStream_t stream) {
-    auto kern = knn_filter_kernel<KP, IS_L2, TF32>;
-    constexpr int smem = smem_bytes(KP);
+    auto kern = knn_filter_kernel<KP, IS_L2, TF32, TWO>;
+    constexpr int smem = smem_bytes(KP, TWO);
     static bool attr_set = false;
     if (!attr_set) {
         B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    kern<<<grid, NUM_THREADS, smem, stream>>>(tq, tx, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = TWO ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B2_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tx, p));
     B2_LAUNCH_CHECK();
     g_stats[ST_FILTER_LAUNCHES]++;
     return B2_OK;
 }
 
-template <int KP>
+template <int KP, bool TWO>
 int launch_kp(bool is_l2, bool tf32, const CUtensorMap& tq, const CUtensorMap& tx, const FilterParams& p, int grid,
               cudaStream_t stream) {
     if (is_l2) {
-        return tf32 ? launch_variant<KP, true, true>(tq, tx, p, grid, stream)
-                    : launch_variant<KP, true, false>(tq, tx, p, grid, stream);
+        return tf32 ? launch_variant<KP, true, true, TWO>(tq, tx, p, grid, stream)
+                    : launch_variant<KP, true, false, TWO>(tq, tx, p, grid, stream);
     }
-    return tf32 ? launch_variant<KP, false, true>(tq, tx, p, grid, stream)
-                : launch_variant<KP, false, false>(tq, tx, p, grid, stream);
+    return tf32 ? launch_variant<KP, false, true, TWO>(tq, tx, p, grid, stream)
+                : launch_variant<KP, false, false, TWO>(tq, tx, p, grid, stream);
+}
+
+template <bool TWO>
+int launch_two(int kp, bool is_l2, bool tf32, const CUtensorMap& tq, const CUtensorMap& tx, const FilterParams& p, int grid,
+               cudaStream_t stream) {
+    switch (kp) {
+        case 16: return launch_kp<16, TWO>(is_l2, tf32, tq, tx, p, grid, stream);
+        case 32: return launch_kp<32, TWO>(is_l2, tf32, tq, tx, p, grid, stream);
+        case 64: return launch_kp<64, TWO>(is_l2, tf32, tq, tx, p, grid, stream);
+        case 96: return launch_kp<96, TWO>(is_l2, tf32, tq, tx, p, grid, stream);
+        default: set_error("internal: unsupported candidate capacity %d", kp); return B2_EINVAL;
+    }
 }
 
 int sm_count(int device) {
@@ -692,9 +826,22 @@ int filter_kp_for_k(int k) {
     return 0;
 }
 
-// Number of corpus splits: enough work items to fill the machine, and few idle SMs in the last wave.
-int filter_choose_splits(int64_t nq, int64_t n, int num_sms) {
+// cta_group::2 (CTA pairs) needs at least two query tiles; B2_FILTER_2CTA=0/1 overrides the default.
+bool filter_use_pair(int64_t nq) {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("B2_FILTER_2CTA");
+        mode = e ? (atoi(e) != 0 ? 1 : 0) : 0;
+    }
+    return mode == 1 && ceil_div(nq, BLOCK_M) >= 2;
+}
+
+// Number of corpus splits: enough work items to fill the machine, and few idle workers in the last wave.
+// In pair mode a worker is a CTA pair and a query unit is two query tiles.
+int filter_choose_splits(int64_t nq, int64_t n, int num_sms, bool two_cta) {
     const int64_t n_mtiles = ceil_div(nq, BLOCK_M);
+    const int64_t n_units = two_cta ? ceil_div(n_mtiles, 2) : n_mtiles;
+    const int64_t workers = two_cta ? std::max(1, num_sms / 2) : num_sms;
     const int64_t n_ntiles = ceil_div(n, BLOCK_N);
     int best = 1;
     double best_eff = -1.0;
@@ -702,9 +849,9 @@ int filter_choose_splits(int64_t nq, int64_t n, int num_sms) {
         const int64_t tps = ceil_div(n_ntiles, s);
         const int64_t s_eff = ceil_div(n_ntiles, tps);  // splits that actually receive tiles
         if (s_eff != s) continue;
-        const int64_t items = n_mtiles * s;
-        const int64_t waves = ceil_div(items, num_sms);
-        double eff = (double)items / (double)(waves * num_sms);
+        const int64_t items = n_units * s;
+        const int64_t waves = ceil_div(items, workers);
+        double eff = (double)items / (double)(waves * workers);
         // each split restarts its candidate lists and adds finalize work: prefer fewer, longer splits
         if (tps < 4 && s > 1) eff -= 0.25;
         eff -= 0.002 * s;
@@ -712,13 +859,13 @@ int filter_choose_splits(int64_t nq, int64_t n, int num_sms) {
             best_eff = eff;
             best = s;
         }
-        if (items >= 8 * (int64_t)num_sms && eff > 0.93) break;
+        if (items >= 8 * workers && eff > 0.93) break;
     }
     return best;
 }
 
 int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int64_t nq, int metric, int kp,
-                      int n_splits, float* cand_score, int32_t* cand_id, float* cand_thr, int device,
+                      int n_splits, bool two_cta, float* cand_score, int32_t* cand_id, float* cand_thr, int device,
                       cudaStream_t stream) {
     if (nq <= 0 || X.n <= 0) return B2_OK;
     if (X.n > 0x7fffff00LL || nq > 0x7fffff00LL) {
@@ -729,7 +876,8 @@ int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int
     const int kb_elems = tf32 ? 32 : 64;
     CUtensorMap tq, tx;
     B2_TRY(make_tmap(&tq, q_filt, tf32, nq, X.d, q_pitch, BLOCK_M));
-    B2_TRY(make_tmap(&tx, X.filt, tf32, X.n, X.d, X.filt_pitch, BLOCK_N));
+    // pair mode: each CTA of the pair loads HALF of the 256-row corpus tile
+    B2_TRY(make_tmap(&tx, X.filt, tf32, X.n, X.d, X.filt_pitch, two_cta ? BLOCK_N / 2 : BLOCK_N));
     FilterParams p;
     p.xnorm = X.norm2;
     p.cand_score = cand_score;
@@ -739,6 +887,7 @@ int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int
     p.n = (int32_t)X.n;
     p.num_kb = (int32_t)ceil_div(X.d, kb_elems);
     p.n_mtiles = (int32_t)ceil_div(nq, BLOCK_M);
+    p.n_munits = two_cta ? (p.n_mtiles + 1) / 2 : p.n_mtiles;
     p.n_ntiles = (int32_t)ceil_div(X.n, BLOCK_N);
     p.tiles_per_split = (int32_t)ceil_div(p.n_ntiles, n_splits);
     p.n_splits = n_splits;
@@ -753,20 +902,18 @@ int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int
         set_error("internal: empty corpus split (tiles %d, splits %d)", p.n_ntiles, n_splits);
         return B2_EINVAL;
     }
-    const int64_t items = (int64_t)p.n_mtiles * n_splits;
-    const int grid = (int)std::min<int64_t>(items, sm_count(device));
+    const int64_t items = (int64_t)p.n_munits * n_splits;
     const bool is_l2 = metric == B2_METRIC_L2;
     if (is_l2 && !X.norm2) {
         set_error("internal: L2 filter without row norms");
         return B2_EINVAL;
     }
-    switch (kp) {
-        case 16: return launch_kp<16>(is_l2, tf32, tq, tx, p, grid, stream);
-        case 32: return launch_kp<32>(is_l2, tf32, tq, tx, p, grid, stream);
-        case 64: return launch_kp<64>(is_l2, tf32, tq, tx, p, grid, stream);
-        case 96: return launch_kp<96>(is_l2, tf32, tq, tx, p, grid, stream);
-        default: set_error("internal: unsupported candidate capacity %d", kp); return B2_EINVAL;
+    if (two_cta) {
+        const int pairs = (int)std::min<int64_t>(items, sm_count(device) / 2);
+        return launch_two<true>(kp, is_l2, tf32, tq, tx, p, 2 * pairs, stream);
     }
+    const int grid = (int)std::min<int64_t>(items, sm_count(device));
+    return launch_two<false>(kp, is_l2, tf32, tq, tx, p, grid, stream);
 }
 
 // All pairs i < j of X whose filter inner product exceeds thr (sem_dedup). Candidates land in pair_i/pair_j (device,
@@ -789,6 +936,7 @@ int launch_pair_filter(const MatView& X, float thr, int part, int nparts, int32_
     p.n = (int32_t)X.n;
     p.num_kb = (int32_t)ceil_div(X.d, kb_elems);
     p.n_mtiles = (int32_t)ceil_div(X.n, BLOCK_M);
+    p.n_munits = p.n_mtiles;
     p.n_ntiles = (int32_t)ceil_div(X.n, BLOCK_N);
     p.n_splits = 1;
     p.tiles_per_split = p.n_ntiles;
