@@ -145,6 +145,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// 32 lanes x 64 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- CTA-pair (cta_group::2) variants ------------------------------------------------------------------------
@@ -236,6 +244,7 @@ struct FilterParams {
     // all-pairs (dedup) schedule: the query matrix IS the corpus; item i is query tile part + i*nparts and sweeps
     // only the corpus tiles that can hold a column j > i (upper triangle)
     int32_t pair_mode, part, nparts;
+    int32_t debug_mode;  // timing experiments only (B2_FILTER_DEBUG): 1 = epilogue drains TMEM but ignores the scores
     float pair_thr;                   // emit candidates with filter score > pair_thr
     int32_t* pair_i;                  // [pair_cap]
     int32_t* pair_j;
@@ -471,6 +480,91 @@ __device__ __noinline__ float2 flush_pending(float* my_sc, int32_t* my_id, const
     return make_float2(thr, __int_as_float(minpos));
 }
 
+// Eight consecutive scores of one query row: append those above `thr` (from position j_start on) to the row's pending
+// buffer. Out of line on purpose: it is the bulk of the rare path and is shared by all 16 call sites.
+// Returns (new pending count, first position that did not fit, or 8).
+__device__ __noinline__ int2 append8(float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7, int idx0,
+                                     int j_start, float thr, int cnt, float* pend_sc, int32_t* pend_id) {
+    int lost = 8;
+#define B2_APPEND(J, V)                                   \
+    if ((J) >= j_start && (V) > thr) {                    \
+        if (cnt < PEND) {                                 \
+            pend_sc[cnt * BLOCK_M] = (V);                 \
+            pend_id[cnt * BLOCK_M] = idx0 + (J);          \
+            ++cnt;                                        \
+        } else {                                          \
+            lost = min(lost, (J));                        \
+        }                                                 \
+    }
+    B2_APPEND(0, v0)
+    B2_APPEND(1, v1)
+    B2_APPEND(2, v2)
+    B2_APPEND(3, v3)
+    B2_APPEND(4, v4)
+    B2_APPEND(5, v5)
+    B2_APPEND(6, v6)
+    B2_APPEND(7, v7)
+#undef B2_APPEND
+    return make_int2(cnt, lost);
+}
+
+// One 32-row x 64-column block of scores (thread = row, v = its 64 scores): find the 8-column groups in which ANY row
+// beats its threshold with a single warp-wide OR reduction, and run the append code only for those.
+template <int KP, bool IS_L2>
+__device__ __forceinline__ void process_chunk64(float (&v)[64], int idx0, int valid, const float* xn, float* my_sc, int32_t* my_id,
+                                                float* pend_sc, int32_t* pend_id, float& thr, int& minpos, int& cnt) {
+    if (valid <= 0) return;  // warp-uniform
+    if constexpr (IS_L2) {
+        const float4* xn4 = reinterpret_cast<const float4*>(xn);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float4 x4 = xn4[j];  // warp-uniform address: broadcast
+            v[4 * j + 0] = fmaf(2.f, v[4 * j + 0], -x4.x);
+            v[4 * j + 1] = fmaf(2.f, v[4 * j + 1], -x4.y);
+            v[4 * j + 2] = fmaf(2.f, v[4 * j + 2], -x4.z);
+            v[4 * j + 3] = fmaf(2.f, v[4 * j + 3], -x4.w);
+        }
+    }
+    if (valid < 64) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j)
+            if (j >= valid) v[j] = -INFINITY;
+    }
+    float gm[8];
+    unsigned mine = 0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        float m = v[8 * g];
+#pragma unroll
+        for (int jj = 1; jj < 8; ++jj) m = fmaxf(m, v[8 * g + jj]);
+        gm[g] = m;
+        mine |= (m > thr ? 1u : 0u) << g;
+    }
+    const unsigned active = __reduce_or_sync(0xffffffffu, mine);
+    if (active == 0) return;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        if (!(active & (1u << g))) continue;  // warp-uniform
+        int j_start = 0;
+        while (true) {  // warp-uniform loop; a second trip only after a pending buffer overflowed inside the group
+            int lost = 8;
+            if (gm[g] > thr) {
+                const int2 r = append8(v[8 * g + 0], v[8 * g + 1], v[8 * g + 2], v[8 * g + 3], v[8 * g + 4], v[8 * g + 5],
+                                       v[8 * g + 6], v[8 * g + 7], idx0 + 8 * g, j_start, thr, cnt, pend_sc, pend_id);
+                cnt = r.x;
+                lost = r.y;
+            }
+            if (!__any_sync(0xffffffffu, cnt >= PEND)) break;
+            const float2 fr = flush_pending<KP>(my_sc, my_id, pend_sc, pend_id, cnt, thr, minpos);
+            thr = fr.x;
+            minpos = __float_as_int(fr.y);
+            cnt = 0;
+            if (!__any_sync(0xffffffffu, lost < 8)) break;
+            j_start = lost;  // re-offer what did not fit (now against the tighter threshold)
+        }
+    }
+}
+
 template <int KP, bool IS_L2, bool TF32, bool TWO>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
@@ -535,12 +629,21 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
                 const int ncols = min(BLOCK_N, p.n - col0);
+                const float* xn_tile = s_xn + acc * BLOCK_N;
+                // four 64-column chunks, TMEM loads software-pipelined one chunk ahead (va / vb ping-pong)
+                float va[64], vb[64];
+                tmem_ld64(taddr, va);
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 32; ++c) {
-                    float v[32];
-                    tmem_ld32(taddr + c * 32, v);
-                    tmem_ld_wait();
-                    if (c == BLOCK_N / 32 - 1) {
+                for (int h = 0; h < 2; ++h) {
+                    tmem_ld_wait();                            // chunk 2h is in va
+                    tmem_ld64(taddr + (2 * h + 1) * 64, vb);   // chunk 2h+1 in flight while va is processed
+                    if (p.debug_mode != 1)
+                        process_chunk64<KP, IS_L2>(va, col0 + (2 * h) * 64, ncols - (2 * h) * 64, xn_tile + (2 * h) * 64, my_sc, my_id,
+                                                   pend_sc, pend_id, thr, minpos, cnt);
+                    tmem_ld_wait();                            // chunk 2h+1 is in vb
+                    if (h == 0) {
+                        tmem_ld64(taddr + 128, va);            // chunk 2 in flight while vb is processed
+                    } else {
                         // whole accumulator stage now in registers: hand TMEM back to the (leader's) MMA warp
                         tc_fence_before();
                         __syncwarp();
@@ -549,67 +652,10 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                             else mbar_arrive(&tmem_empty[acc]);
                         }
                     }
-                    if constexpr (IS_L2) {
-                        const float4* xn4 = reinterpret_cast<const float4*>(s_xn + acc * BLOCK_N + c * 32);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 x4 = xn4[j];  // warp-uniform address: broadcast
-                            v[4 * j + 0] = fmaf(2.f, v[4 * j + 0], -x4.x);
-                            v[4 * j + 1] = fmaf(2.f, v[4 * j + 1], -x4.y);
-                            v[4 * j + 2] = fmaf(2.f, v[4 * j + 2], -x4.z);
-                            v[4 * j + 3] = fmaf(2.f, v[4 * j + 3], -x4.w);
-                        }
-                    }
-                    const int valid = ncols - c * 32;  // warp-uniform
-                    if (valid <= 0) continue;
-                    if (valid < 32) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j >= valid) v[j] = -INFINITY;
-                    }
-                    // gate in two levels: the whole 32x32 block, then 8-column groups. Only groups in which some row
-                    // has a score above its threshold run the (long) predicated append code.
-                    float gm[4];
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        float m = v[8 * g];
-#pragma unroll
-                        for (int jj = 1; jj < 8; ++jj) m = fmaxf(m, v[8 * g + jj]);
-                        gm[g] = m;
-                    }
-                    const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
-                    if (!__any_sync(0xffffffffu, mx > thr)) continue;
-                    const int idx0 = col0 + c * 32;
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        if (!__any_sync(0xffffffffu, gm[g] > thr)) continue;
-                        int j_start = 8 * g;
-                        while (true) {  // warp-uniform loop; a second trip only after a buffer overflowed mid-group
-                            int lost_at = 32;
-                            if (gm[g] > thr) {
-#pragma unroll
-                                for (int jj = 0; jj < 8; ++jj) {
-                                    const int j = 8 * g + jj;
-                                    if (j >= j_start && v[j] > thr) {
-                                        if (cnt < PEND) {
-                                            pend_sc[cnt * BLOCK_M] = v[j];
-                                            pend_id[cnt * BLOCK_M] = idx0 + j;
-                                            ++cnt;
-                                        } else {
-                                            lost_at = min(lost_at, j);
-                                        }
-                                    }
-                                }
-                            }
-                            if (!__any_sync(0xffffffffu, cnt >= PEND)) break;
-                            const float2 fr = flush_pending<KP>(my_sc, my_id, pend_sc, pend_id, cnt, thr, minpos);
-                            thr = fr.x;
-                            minpos = __float_as_int(fr.y);
-                            cnt = 0;
-                            if (!__any_sync(0xffffffffu, lost_at < 32)) break;
-                            j_start = lost_at;  // re-offer what did not fit (now against the tighter threshold)
-                        }
-                    }
+                    if (p.debug_mode != 1)
+                        process_chunk64<KP, IS_L2>(vb, col0 + (2 * h + 1) * 64, ncols - (2 * h + 1) * 64, xn_tile + (2 * h + 1) * 64, my_sc,
+                                                   my_id, pend_sc, pend_id, thr, minpos, cnt);
+                    else if (vb[0] == 12345.678f) thr = va[1] + vb[1];  // keep the loads alive in the timing experiment
                 }
                 if (++acc == 2) {
                     acc = 0;
@@ -894,6 +940,14 @@ int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int
     p.pair_mode = 0;
     p.part = 0;
     p.nparts = 1;
+    {
+        static int dbg = -1;
+        if (dbg < 0) {
+            const char* e = getenv("B2_FILTER_DEBUG");
+            dbg = e ? atoi(e) : 0;
+        }
+        p.debug_mode = dbg;
+    }
     p.pair_thr = 0.f;
     p.pair_i = p.pair_j = nullptr;
     p.pair_count = nullptr;
