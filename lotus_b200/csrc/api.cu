@@ -126,7 +126,7 @@ int search_core(b2_index* idx, const MatView& X, int metric, const void* q_dev, 
         const void* q_filt = q_in_place ? static_cast<const void*>(qc) : idx->q_filt.p;
         B2_TRY(idx->cand_score.ensure((size_t)nqc * n_splits * kp * sizeof(float)));
         B2_TRY(idx->cand_id.ensure((size_t)nqc * n_splits * kp * sizeof(int32_t)));
-        B2_TRY(idx->cand_thr.ensure((size_t)nqc * n_splits * sizeof(float)));
+        B2_TRY(idx->cand_thr.ensure((size_t)nqc * n_splits * 2 * sizeof(float)));  // two epilogue sets per split
         B2_TRY(idx->flags.ensure((size_t)nqc * sizeof(int32_t)));
         B2_TRY(idx->h_flags.ensure((size_t)nqc * sizeof(int32_t)));
         if (!q_in_place) B2_TRY(launch_prep_queries(qc, q_dtype, nqc, X.d, idx->q_filt.p, filt_dtype, q_pitch, st));
@@ -134,7 +134,7 @@ int search_core(b2_index* idx, const MatView& X, int metric, const void* q_dev, 
         B2_TRY(launch_knn_filter(X, q_filt, q_pitch, nqc, metric, kp, n_splits, two_cta, idx->cand_score.as<float>(),
                                  idx->cand_id.as<int32_t>(), idx->cand_thr.as<float>(), idx->device, st));
         B2_CUDA(cudaEventRecord(idx->ev1, st));
-        B2_TRY(launch_finalize(X, qc, q_dtype, nqc, metric, k, kp, n_splits, idx->cand_score.as<float>(),
+        B2_TRY(launch_finalize(X, qc, q_dtype, nqc, metric, k, kp, kp / 2, 2 * n_splits, idx->cand_score.as<float>(),
                                idx->cand_id.as<int32_t>(), idx->cand_thr.as<float>(), rel_eps, id_map, id_offset, osc, oid,
                                idx->flags.as<int32_t>(), st));
         B2_CUDA(cudaMemcpyAsync(idx->h_flags.p, idx->flags.p, (size_t)nqc * sizeof(int32_t), cudaMemcpyDeviceToHost, st));

@@ -115,8 +115,8 @@ int launch_convert_pad(const void* x, int dtype, int64_t n, int d, void* out, in
                        cudaStream_t stream);
 int launch_gather_rows(const void* x, int dtype, int d, const int64_t* ids, int64_t m, int64_t n, void* out,
                        int* err_flag, cudaStream_t stream);
-int launch_finalize(const MatView& X, const void* q, int q_dtype, int64_t nq, int metric, int k, int kp,
-                    int n_splits, const float* cand_score, const int32_t* cand_id, const float* cand_thr,
+int launch_finalize(const MatView& X, const void* q, int q_dtype, int64_t nq, int metric, int k, int kp, int list_len,
+                    int n_lists, const float* cand_score, const int32_t* cand_id, const float* cand_thr,
                     float rel_eps, const int64_t* id_map, int64_t id_offset, float* out_scores, int64_t* out_idx,
                     int32_t* flags, cudaStream_t stream);
 int launch_dense_topk(const MatView& X, const void* q, int q_dtype, int64_t nq, const int32_t* q_sel,

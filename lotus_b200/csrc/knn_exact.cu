@@ -198,7 +198,8 @@ struct FinalizeParams {
     int32_t* flags;
     int64_t nq;
     int64_t id_offset;
-    int32_t d, dtype, q_dtype, metric, k, kp, n_splits;
+    int32_t d, dtype, q_dtype, metric, k, kp, n_splits;  // n_splits = number of candidate lists per query, kp = survivors kept
+    int32_t list_len;                                    // entries per candidate list (<= 32*R)
     float rel_eps, max_norm;
 };
 
@@ -239,13 +240,13 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(const Finalize
     for (int r = 0; r < 2 * R; ++r) keys[r] = KEY_WORST;
     float bound = -INFINITY;
     for (int s = 0; s < p.n_splits; ++s) {
-        const size_t lbase = ((size_t)q * p.n_splits + s) * p.kp;
+        const size_t lbase = ((size_t)q * p.n_splits + s) * p.list_len;
         bound = fmaxf(bound, p.cand_thr[(size_t)q * p.n_splits + s]);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int e = r * 32 + lane;
             uint64_t kk = KEY_WORST;
-            if (e < p.kp) {
+            if (e < p.list_len) {
                 const int32_t id = p.cand_id[lbase + e];
                 if (id >= 0) kk = ((uint64_t)(~f32_ord(p.cand_score[lbase + e])) << 32) | (uint32_t)id;
             }
@@ -693,7 +694,7 @@ static int launch_finalize_r(const FinalizeParams& p, cudaStream_t stream) {
     return B2_OK;
 }
 
-int launch_finalize(const MatView& X, const void* q, int q_dtype, int64_t nq, int metric, int k, int kp,
+int launch_finalize(const MatView& X, const void* q, int q_dtype, int64_t nq, int metric, int k, int kp, int list_len,
                     int n_splits, const float* cand_score, const int32_t* cand_id, const float* cand_thr,
                     float rel_eps, const int64_t* id_map, int64_t id_offset, float* out_scores, int64_t* out_idx,
                     int32_t* flags, cudaStream_t stream) {
@@ -716,6 +717,7 @@ int launch_finalize(const MatView& X, const void* q, int q_dtype, int64_t nq, in
     p.metric = metric;
     p.k = k;
     p.kp = kp;
+    p.list_len = list_len;
     p.n_splits = n_splits;
     p.rel_eps = rel_eps;
     p.max_norm = X.max_norm;
