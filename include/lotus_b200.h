@@ -141,6 +141,13 @@ B2_API int b2_kmeans(b2_index* idx, const int64_t* ids, int64_t m, int32_t k, in
 B2_API int b2_kmeans_assign(b2_index* idx, const int64_t* ids, int64_t m, const float* centroids, int32_t k,
                      int64_t* out_assign, float* out_dist);
 
+/* per-shard centroid update for multi-GPU Lloyd: for the rows ids[0..m) (or all) and their assignment assign[m],
+ * out_sums[k,d] float32 = sum of the member rows of each centroid (point order, fp32, NOT divided), out_counts[k] float32.
+ * The caller all-reduces sums and counts over the ranks and divides. HOST buffers. (faiss/Clustering.cpp compute_centroids
+ * before its normalisation loop; lotus/utils.py:61-62 calls it through faiss.Kmeans.train.) */
+B2_API int b2_kmeans_accumulate(b2_index* idx, const int64_t* ids, int64_t m, const int64_t* assign, int32_t k, float* out_sums,
+                         float* out_counts);
+
 /* ---- instrumentation ---------------------------------------------------------------------------------- */
 /* counters since the last b2_stats_reset(): [0] kernels launched by this library, [1] queries answered,
  * [2] queries that took the exact dense fallback, [3] tcgen05 filter launches, [4] rows rescored exactly.

@@ -20,7 +20,7 @@ SYMBOLS = [
     "b2_abi_version", "b2_last_error", "b2_device_count", "b2_max_k", "b2_index_create", "b2_index_free",
     "b2_index_ntotal", "b2_index_dim", "b2_index_dtype", "b2_index_metric", "b2_index_device", "b2_index_data_dev",
     "b2_index_search", "b2_index_search_dev", "b2_merge_topk_dev", "b2_index_gather", "b2_threshold_pairs",
-    "b2_connected_components", "b2_kmeans", "b2_kmeans_assign", "b2_stats", "b2_stats_reset", "b2_last_filter_ms",
+    "b2_connected_components", "b2_kmeans", "b2_kmeans_assign", "b2_kmeans_accumulate", "b2_stats", "b2_stats_reset", "b2_last_filter_ms",
 ]
 
 
@@ -74,6 +74,8 @@ def lib() -> ctypes.CDLL:
     L.b2_kmeans.argtypes = [vp, vp, i64, i32, i32, i64, i32, vp, vp, vp]
     L.b2_kmeans_assign.restype = c.c_int
     L.b2_kmeans_assign.argtypes = [vp, vp, i64, vp, i32, vp, vp]
+    L.b2_kmeans_accumulate.restype = c.c_int
+    L.b2_kmeans_accumulate.argtypes = [vp, vp, i64, vp, i32, vp, vp]
     L.b2_stats.restype = c.c_int
     L.b2_stats.argtypes = [c.POINTER(i64), i32]
     L.b2_stats_reset.restype = None
@@ -223,6 +225,19 @@ class Index:
         dist = np.empty(m, dtype=np.float32)
         check(lib().b2_kmeans_assign(self._h, _ptr(ids_a), m, _ptr(c), c.shape[0], _ptr(assign), _ptr(dist)))
         return assign, dist
+
+
+def _index_kmeans_accumulate(self, assign, k: int, ids=None):
+    """Per-shard centroid sums [k,d] (point order, fp32, not normalised) and counts [k] for multi-GPU Lloyd."""
+    a = np.ascontiguousarray(assign, dtype=np.int64)
+    ids_a = None if ids is None else np.ascontiguousarray(ids, dtype=np.int64)
+    sums = np.empty((k, self.d), dtype=np.float32)
+    counts = np.empty(k, dtype=np.float32)
+    check(lib().b2_kmeans_accumulate(self._h, _ptr(ids_a), len(a), _ptr(a), k, _ptr(sums), _ptr(counts)))
+    return sums, counts
+
+
+Index.kmeans_accumulate = _index_kmeans_accumulate
 
 
 def connected_components(n: int, pi: np.ndarray, pj: np.ndarray, device: int = 0) -> np.ndarray:

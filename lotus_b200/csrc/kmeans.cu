@@ -110,7 +110,7 @@ __global__ void km_fill_kernel(const int64_t* assign, int64_t n, int64_t L, int 
 
 // thread (c, j): centroid[c][j] = (sum over members of c, in point order, of x[p][j]) * (1 / count)   [all fp32]
 __global__ void km_accumulate_kernel(const void* x, int dtype, int d, const int64_t* ids, const int32_t* members,
-                                     const int64_t* offsets, float* centroids, float* hassign) {
+                                     const int64_t* offsets, float* centroids, float* hassign, int normalize) {
     const int c = blockIdx.x;
     const int64_t o0 = offsets[c], o1 = offsets[c + 1];
     const float cntf = (float)(o1 - o0);
@@ -138,7 +138,7 @@ __global__ void km_accumulate_kernel(const void* x, int dtype, int d, const int6
                                         : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[r * d + j]);
         acc = __fadd_rn(acc, v);
     }
-    if (o1 > o0) {
+    if (normalize && o1 > o0) {
         const float norm = __fdiv_rn(1.0f, cntf);
         acc = __fmul_rn(acc, norm);
     }
@@ -228,7 +228,7 @@ int assign_points(b2_index* idx, const void* pts, int64_t m, const float* cent, 
 }
 
 int update_centroids(b2_index* idx, const void* x, const int64_t* row_ids, int64_t n, const int64_t* assign, int k, KmWork& w,
-                     float* cent, cudaStream_t st) {
+                     float* cent, cudaStream_t st, int normalize = 1) {
     const int d = idx->d;
     int64_t nb = std::min<int64_t>(4096, std::max<int64_t>(1, ceil_div(n, 256)));
     while (nb > 1 && nb * (int64_t)k > ((int64_t)1 << 26)) nb /= 2;
@@ -258,7 +258,7 @@ int update_centroids(b2_index* idx, const void* x, const int64_t* row_ids, int64
     B2_LAUNCH_CHECK();
     dim3 grid((unsigned)k, (unsigned)ceil_div(d, 128));
     km_accumulate_kernel<<<grid, 128, 0, st>>>(x, idx->dtype, d, row_ids, w.members.as<int32_t>(), w.offsets.as<int64_t>(), cent,
-                                               w.hassign.as<float>());
+                                               w.hassign.as<float>(), normalize);
     B2_LAUNCH_CHECK();
     return B2_OK;
 }
@@ -395,6 +395,48 @@ int b2_kmeans(b2_index* idx, const int64_t* ids, int64_t m, int32_t k, int32_t n
     const int rc = kmeans_impl(idx, ids, m, k, niter, seed, full_lloyd, out_assign, out_centroids, out_obj, w);
     cudaStreamSynchronize(idx->stream);
     w.release();
+    return rc;
+}
+
+int b2_kmeans_accumulate(b2_index* idx, const int64_t* ids, int64_t m, const int64_t* assign, int32_t k, float* out_sums,
+                         float* out_counts) {
+    if (!idx) { set_error("Index not loaded"); return B2_EINVAL; }
+    if (!ids) m = idx->n;
+    if (k <= 0 || m < 0 || !assign || !out_sums || !out_counts) { set_error("bad arguments"); return B2_EINVAL; }
+    for (int64_t i = 0; i < m; ++i) {
+        if (assign[i] < 0 || assign[i] >= k) { set_error("assign[%lld] = %lld outside [0, %d)", (long long)i, (long long)assign[i], k); return B2_ERANGE; }
+        if (ids && (ids[i] < 0 || ids[i] >= idx->n)) { set_error("ids contains a position outside [0, %lld)", (long long)idx->n); return B2_ERANGE; }
+    }
+    DeviceGuard guard(idx->device);
+    cudaStream_t st = idx->stream;
+    KmWork w;
+    DevBuf d_assign;
+    int rc = w.cent.ensure((size_t)k * idx->d * sizeof(float));
+    if (rc == B2_OK) rc = d_assign.ensure((size_t)std::max<int64_t>(m, 1) * sizeof(int64_t));
+    const int64_t* ids_dev = nullptr;
+    if (rc == B2_OK && ids) {
+        rc = w.ids.ensure((size_t)std::max<int64_t>(m, 1) * sizeof(int64_t));
+        if (rc == B2_OK) {
+            cudaMemcpyAsync(w.ids.p, ids, (size_t)m * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+            ids_dev = w.ids.as<int64_t>();
+        }
+    }
+    if (rc == B2_OK) {
+        cudaMemcpyAsync(d_assign.p, assign, (size_t)m * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+        rc = update_centroids(idx, idx->store.p, ids_dev, m, d_assign.as<int64_t>(), k, w, w.cent.as<float>(), st, /*normalize=*/0);
+    }
+    if (rc == B2_OK) {
+        cudaMemcpyAsync(out_sums, w.cent.p, (size_t)k * idx->d * sizeof(float), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(out_counts, w.hassign.p, (size_t)k * sizeof(float), cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) {
+            set_error("k-means accumulate failed on the device: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = B2_ECUDA;
+        }
+    } else {
+        cudaStreamSynchronize(st);
+    }
+    w.release();
+    d_assign.release();
     return rc;
 }
 

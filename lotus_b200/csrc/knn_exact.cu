@@ -265,14 +265,31 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(const Finalize
             if (first_drop != KEY_WORST) bound = fmaxf(bound, f32_unord(~(uint32_t)(first_drop >> 32)));
         }
     }
+    if (p.n_splits == 1) warp_bitonic_sort<2 * R>(keys, lane);  // a single list arrives unsorted
+    // margin between a filter score and the exact score it stands for (same quantity the certificate uses below)
+    const double qn_m = sqrt(qn2), mx_m = (double)p.max_norm;
+    const double eps_f = is_l2 ? 2.0 * (double)p.rel_eps * qn_m * mx_m + 2.4e-7 * (mx_m * mx_m + 2.0 * qn_m * mx_m) + 1e-30
+                               : (double)p.rel_eps * qn_m * mx_m + 1e-30;
+    // Pruning before the (expensive) re-score: the k best survivors BY FILTER SCORE have exact scores >= t_k - eps, so a
+    // survivor whose filter score is below t_k - 2 eps is strictly worse than k others: it cannot enter or tie the top k.
+#pragma unroll
+    for (int r = 0; r < R; ++r) s_ex[r * 32 + lane] = keys[r] == KEY_WORST ? -INFINITY : f32_unord(~(uint32_t)(keys[r] >> 32));
+    __syncwarp();
+    float cut = -INFINITY;
+    if (p.k <= NC) {
+        const float tk = s_ex[p.k - 1];
+        if (tk > -INFINITY) cut = (float)((double)tk - 2.0 * eps_f - 4.8e-7 * fabs((double)tk));
+    }
+    __syncwarp();
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int e = r * 32 + lane;
-        s_id[e] = keys[r] == KEY_WORST ? -1 : (int32_t)(uint32_t)(keys[r] & 0xffffffffu);
+        const bool keep = keys[r] != KEY_WORST && f32_unord(~(uint32_t)(keys[r] >> 32)) >= cut;
+        s_id[e] = keep ? (int32_t)(uint32_t)(keys[r] & 0xffffffffu) : -1;
     }
     __syncwarp();
 
-    // 3. canonical re-scoring of the NC survivors, four rows in flight
+    // 3. canonical re-scoring of the surviving candidates, four rows in flight
     for (int c0 = 0; c0 < NC; c0 += 4) {
         double part[4];
         int32_t ids[4];

@@ -101,3 +101,108 @@ def merge_host_lists(scores: np.ndarray, idx: np.ndarray, metric: int):
                 out_s[q, o] = pad
                 out_i[q, o] = -1
     return out_s, out_i
+
+
+# ---- multi-GPU dedup and k-means ----------------------------------------------------------------------
+def sharded_threshold_pairs(index: "nv.Index", threshold: float, group=None):
+    """All pairs i<j with score > threshold when EVERY rank holds the full corpus in `index` (it fits: 7.7 GB for
+    10M x 384 bf16): the upper-triangular tile grid is dealt round-robin to the ranks (`part`/`nparts` of
+    b2_threshold_pairs), each rank filters + verifies its tiles, then one all-gather of the sparse pair lists.
+    Returns the same (pi, pj) — sorted by (i, j) — on every rank."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    pi, pj = index.threshold_pairs(threshold, part=rank, nparts=world)
+    if world == 1:
+        return pi, pj
+    dev = torch.device("cuda", index.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    cnt = torch.tensor([len(pi)], dtype=torch.int64, device=dev)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(cnts, cnt, group=group)
+    cap = int(max(int(c.item()) for c in cnts))
+    buf = torch.full((2, max(cap, 1)), -1, dtype=torch.int64, device=dev)
+    buf[0, :len(pi)] = torch.from_numpy(pi).to(dev)
+    buf[1, :len(pj)] = torch.from_numpy(pj).to(dev)
+    bufs = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(bufs, buf, group=group)
+    ai = np.concatenate([b[0, :int(c.item())].cpu().numpy() for b, c in zip(bufs, cnts)])
+    aj = np.concatenate([b[1, :int(c.item())].cpu().numpy() for b, c in zip(bufs, cnts)])
+    order = np.lexsort((aj, ai))
+    return ai[order], aj[order]
+
+
+def sharded_kmeans(index: "nv.Index", n_total: int, row_offset: int, k: int, niter: int = 20, seed: int = 1234, group=None):
+    """Full-Lloyd k-means over points row-sharded across ranks (`index` holds this rank's rows [row_offset, row_offset+n_local)).
+    faiss's control flow (lotus/utils.py:61-65 -> faiss/Clustering.cpp): initial centroids = the first k points of
+    rand_perm(n_total, seed+1) (fetched from whichever rank owns them), then per iteration: exact assignment of the local
+    points (b2_kmeans_assign), per-shard point-order fp32 sums (b2_kmeans_accumulate), ONE all-reduce(sum) of the [k,d]
+    sums and [k] counts, division, split_clusters replayed identically on every rank. The cross-rank fp32 reduction
+    makes centroids agree with the single-process restatement to rounding, not bit-for-bit.
+    Returns (local assignment [n_local] int64, centroids [k,d] float32, objective per iteration)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    dev = torch.device("cuda", index.device) if (world > 1 and dist.get_backend(group) == "nccl") else torch.device("cpu")
+    n_local, d = index.n, index.d
+    # initial centroids: rows perm[:k] of the global matrix
+    rng = np.random.RandomState((seed + 1) & 0xFFFFFFFF)
+    raw = rng._bit_generator.random_raw(max(n_total, 1))  # std::mt19937 stream == faiss RandomGenerator
+    perm = np.arange(n_total, dtype=np.int64)
+    for i in range(min(k, n_total - 1)):  # only the first k entries of the Fisher-Yates shuffle are needed
+        i2 = i + int(raw[i]) % (n_total - i)
+        perm[i], perm[i2] = perm[i2], perm[i]
+    want = perm[:k]
+    mine = (want >= row_offset) & (want < row_offset + n_local)
+    cent = np.zeros((k, d), dtype=np.float32)
+    if mine.any():
+        rows = index.gather(want[mine] - row_offset)
+        cent[mine] = nv.bf16_bits_to_f32(rows) if index.dtype == nv.BF16 else rows
+    if world > 1:
+        t = torch.from_numpy(cent).to(dev)
+        dist.all_reduce(t, group=group)  # each row is non-zero on exactly one rank
+        cent = t.cpu().numpy()
+    objs = []
+    for _ in range(niter):
+        assign, dist2 = index.kmeans_assign(cent)
+        sums, counts = index.kmeans_accumulate(assign, k)
+        obj = np.array([float(dist2.astype(np.float64).sum())])
+        if world > 1:
+            ts, tc, to = torch.from_numpy(sums).to(dev), torch.from_numpy(counts).to(dev), torch.from_numpy(obj).to(dev)
+            dist.all_reduce(ts, group=group)
+            dist.all_reduce(tc, group=group)
+            dist.all_reduce(to, group=group)
+            sums, counts, obj = ts.cpu().numpy(), tc.cpu().numpy(), to.cpu().numpy()
+        objs.append(float(obj[0]))
+        nz = counts > 0
+        cent = np.where(nz[:, None], sums * (np.float32(1) / np.where(nz, counts, 1)).astype(np.float32)[:, None], 0).astype(np.float32)
+        if not nz.all():
+            cent, counts = split_clusters_host(cent, counts, n_total)
+    assign, _ = index.kmeans_assign(cent)
+    return assign, cent, np.asarray(objs, dtype=np.float32)
+
+
+def split_clusters_host(centroids: np.ndarray, hassign: np.ndarray, n: int):
+    """faiss/Clustering.cpp split_clusters (EPS = 1/1024, RandomGenerator rng(1234)) on host arrays; every rank replays
+    the same stream so the replicated centroids stay identical."""
+    c = np.ascontiguousarray(centroids, dtype=np.float32).copy()
+    h = np.ascontiguousarray(hassign, dtype=np.float32).copy()
+    k, d = c.shape
+    raw = iter(np.random.RandomState(1234)._bit_generator.random_raw(1 << 16).tolist())
+    eps = 1 / 1024.0
+    even = (np.arange(d) % 2 == 0)
+    for ci in range(k):
+        if h[ci] == 0:
+            cj = 0
+            while True:
+                p = np.float32((np.float64(h[cj]) - 1.0) / np.float64(np.float32(n - k)))
+                r = np.float32(next(raw)) / np.float32(4294967295)
+                if r < p:
+                    break
+                cj = (cj + 1) % k
+            base = c[cj].astype(np.float64)
+            c[ci] = np.where(even, base * (1 + eps), base * (1 - eps)).astype(np.float32)
+            c[cj] = np.where(even, base * (1 - eps), base * (1 + eps)).astype(np.float32)
+            h[ci] = h[cj] / 2
+            h[cj] -= h[ci]
+    return c, h

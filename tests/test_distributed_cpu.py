@@ -78,3 +78,13 @@ def test_merge_rule_on_exact_ties():
     i = np.array([[[0, -1]], [[-1, -1]]], dtype=np.int64)
     ms, mi = merge_host_lists(s, i, 1)
     assert mi.tolist() == [[0, -1]] and ms[0, 1] == np.finfo(np.float32).max
+
+
+def test_split_clusters_host_matches_oracle():
+    import oracle
+    from lotus_b200.distributed import split_clusters_host
+    cent = gauss(6, 10, 3, normalize=False)
+    h = np.array([7, 0, 4, 0, 9, 1], np.float32)
+    c1, h1 = split_clusters_host(cent, h, n=21)
+    c2, h2, ns = oracle.split_clusters(cent, h, n=21)
+    assert ns == 2 and np.array_equal(bits(c1), bits(c2)) and np.array_equal(h1, h2)

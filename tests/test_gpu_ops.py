@@ -192,3 +192,21 @@ def test_merge_topk_kernel_equals_host_rule(gpu):
                                stream=torch.cuda.current_stream().cuda_stream)
             hs, hi = merge_host_lists(sc, ids.astype(np.int64), metric)
             assert np.array_equal(oi.cpu().numpy(), hi) and np.array_equal(bits(os_.cpu().numpy()), bits(hs))
+
+
+def test_kmeans_accumulate_and_sharded_driver_single_rank(gpu):
+    """The multi-GPU Lloyd driver on one rank (world 1): per-shard sums are faiss's point-order fp32 sums, and the driver's
+    full-Lloyd result equals the oracle's full-Lloyd restatement bit for bit."""
+    from lotus_b200.distributed import sharded_kmeans
+    rng = np.random.default_rng(80)
+    centers = gauss(5, 32, 81) * 4
+    x = (centers[rng.integers(0, 5, 1500)] + gauss(1500, 32, 82, normalize=False)).astype(np.float32)
+    idx = gpu.Index(x, gpu.F32, 1)
+    ao, co, oo = oracle.kmeans(x, 5, niter=4, full_lloyd=True)
+    sums, counts = idx.kmeans_accumulate(ao, 5)
+    cref, href = oracle.compute_centroids(x, ao, 5)
+    assert np.array_equal(counts, href)
+    assert np.array_equal(bits(sums * (np.float32(1) / counts)[:, None]), bits(cref))
+    a, c, obj = sharded_kmeans(idx, len(x), 0, 5, niter=4)
+    assert np.array_equal(a, ao) and np.array_equal(bits(c), bits(co)) and np.allclose(obj, oo, rtol=1e-5)
+    idx.close()
