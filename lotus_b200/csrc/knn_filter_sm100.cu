@@ -134,7 +134,6 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
     asm volatile(
@@ -190,14 +189,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-}
-// 32 lanes x 64 consecutive fp32 columns
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
-                 : "r"(taddr)
-                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -509,13 +500,20 @@ __device__ __forceinline__ void teardown_ring(const Ring& r, int alloc_warp) {
     }
 }
 
-// Replace-min insertion into the thread's candidate list (column `row` of sc/id, stride BLOCK_M): overwrite
-// the current minimum, then rescan for the new minimum (= threshold; -inf while a slot is free).
+// Replace-min insertion into the thread's candidate list (column `row` of sc/id, stride BLOCK_M): while slots are
+// free just take the next one; once full, overwrite the current minimum and rescan for the new minimum (= threshold).
 // Called only from flush_pending, where all 32 lanes of the warp run it in lockstep.
 template <int KP>
 __device__ __forceinline__ void list_insert(float* sc, int32_t* id, float s, int32_t idx, float& thr, int& minpos) {
-    sc[minpos * BLOCK_M] = s;
-    id[minpos * BLOCK_M] = idx;
+    // fill phase (minpos < 0 encodes "-(entries so far) - 1"): slots are free, no scan needed until the list is full
+    const bool filling = minpos < 0;
+    const int pos = filling ? -minpos - 1 : minpos;
+    sc[pos * BLOCK_M] = s;
+    id[pos * BLOCK_M] = idx;
+    if (filling && pos + 1 < KP) {
+        minpos = -(pos + 1) - 1;
+        return;  // threshold stays -inf
+    }
     float m = sc[0];
     int mp = 0;
 #pragma unroll 8
@@ -549,36 +547,12 @@ __device__ __noinline__ float2 flush_pending(float* my_sc, int32_t* my_id, const
     return make_float2(thr, __int_as_float(minpos));
 }
 
-// Eight consecutive scores of one query row: append those above `thr` (from position j_start on) to the row's pending
-// buffer. Out of line on purpose: it is the bulk of the rare path and is shared by all 16 call sites.
-// Returns (new pending count, first position that did not fit, or 8).
-__device__ __noinline__ int2 append8(float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7, int idx0,
-                                     int j_start, float thr, int cnt, float* pend_sc, int32_t* pend_id) {
-    int lost = 8;
-#define B2_APPEND(J, V)                                   \
-    if ((J) >= j_start && (V) > thr) {                    \
-        if (cnt < PEND) {                                 \
-            pend_sc[cnt * BLOCK_M] = (V);                 \
-            pend_id[cnt * BLOCK_M] = idx0 + (J);          \
-            ++cnt;                                        \
-        } else {                                          \
-            lost = min(lost, (J));                        \
-        }                                                 \
-    }
-    B2_APPEND(0, v0)
-    B2_APPEND(1, v1)
-    B2_APPEND(2, v2)
-    B2_APPEND(3, v3)
-    B2_APPEND(4, v4)
-    B2_APPEND(5, v5)
-    B2_APPEND(6, v6)
-    B2_APPEND(7, v7)
-#undef B2_APPEND
-    return make_int2(cnt, lost);
-}
-
-// One 32-row x 32-column block of scores (thread = row, v = its 32 scores): find the 8-column groups in which ANY row
-// beats its threshold with a single warp-wide OR reduction, and run the append code only for those.
+// One 32-row x 32-column block of scores (thread = row, v = its 32 scores). Two-level gating keeps the cost proportional
+// to the number of candidates: (1) one warp-wide OR reduction finds the 8-column groups in which ANY row beats its
+// threshold (late in a sweep almost none); (2) inside such a group one ballot per column, and only columns that hold a
+// candidate run the append (early in a sweep thresholds are low and most groups are "active", but most columns of most
+// rows are not). A row's pending buffer is flushed - by the whole warp, in lockstep - as soon as any row's is full, so
+// nothing is ever dropped.
 template <int KPH, bool IS_L2>
 __device__ __forceinline__ void process_chunk32(float (&v)[32], int idx0, int valid, const float* xn, float* my_sc, int32_t* my_id,
                                                 float* pend_sc, int32_t* pend_id, float& thr, int& minpos, int& cnt) {
@@ -599,14 +573,12 @@ __device__ __forceinline__ void process_chunk32(float (&v)[32], int idx0, int va
         for (int j = 0; j < 32; ++j)
             if (j >= valid) v[j] = -INFINITY;
     }
-    float gm[4];
     unsigned mine = 0;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         float m = v[8 * g];
 #pragma unroll
         for (int jj = 1; jj < 8; ++jj) m = fmaxf(m, v[8 * g + jj]);
-        gm[g] = m;
         mine |= (m > thr ? 1u : 0u) << g;
     }
     const unsigned active = __reduce_or_sync(0xffffffffu, mine);
@@ -614,22 +586,22 @@ __device__ __forceinline__ void process_chunk32(float (&v)[32], int idx0, int va
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         if (!(active & (1u << g))) continue;  // warp-uniform
-        int j_start = 0;
-        while (true) {  // warp-uniform loop; a second trip only after a pending buffer overflowed inside the group
-            int lost = 8;
-            if (gm[g] > thr) {
-                const int2 r = append8(v[8 * g + 0], v[8 * g + 1], v[8 * g + 2], v[8 * g + 3], v[8 * g + 4], v[8 * g + 5],
-                                       v[8 * g + 6], v[8 * g + 7], idx0 + 8 * g, j_start, thr, cnt, pend_sc, pend_id);
-                cnt = r.x;
-                lost = r.y;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const float s = v[8 * g + jj];
+            const bool cand = s > thr;
+            if (!__any_sync(0xffffffffu, cand)) continue;  // warp-uniform: no row wants this column
+            if (cand) {
+                pend_sc[cnt * BLOCK_M] = s;
+                pend_id[cnt * BLOCK_M] = idx0 + 8 * g + jj;
+                ++cnt;
             }
-            if (!__any_sync(0xffffffffu, cnt >= PEND)) break;
-            const float2 fr = flush_pending<KPH>(my_sc, my_id, pend_sc, pend_id, cnt, thr, minpos);
-            thr = fr.x;
-            minpos = __float_as_int(fr.y);
-            cnt = 0;
-            if (!__any_sync(0xffffffffu, lost < 8)) break;
-            j_start = lost;  // re-offer what did not fit (now against the tighter threshold)
+            if (__any_sync(0xffffffffu, cnt >= PEND)) {
+                const float2 fr = flush_pending<KPH>(my_sc, my_id, pend_sc, pend_id, cnt, thr, minpos);
+                thr = fr.x;
+                minpos = __float_as_int(fr.y);
+                cnt = 0;
+            }
         }
     }
 }
@@ -687,8 +659,8 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 my_id[i * BLOCK_M] = -1;
             }
             float thr = -INFINITY;
-            int minpos = 0;
-            int cnt = 0;  // pending candidates of this row
+            int minpos = -1;  // fill phase, 0 entries (see list_insert)
+            int cnt = 0;      // pending candidates of this row
             for (int t = t0; t < t1; ++t, ++tile_ctr) {
                 if ((int)(tile_ctr & 1u) != e) continue;  // the other set's tile
                 const int col0 = t * BLOCK_N;
@@ -967,6 +939,19 @@ bool filter_use_pair(int64_t nq) {
 // Number of corpus splits: enough work items to fill the machine, and few idle workers in the last wave.
 // In pair mode a worker is a CTA pair and a query unit is two query tiles.
 int filter_choose_splits(int64_t nq, int64_t n, int num_sms, bool two_cta) {
+    {
+        static int forced = -1;  // B2_FILTER_SPLITS: experiments only
+        if (forced < 0) {
+            const char* e = getenv("B2_FILTER_SPLITS");
+            forced = e ? atoi(e) : 0;
+        }
+        if (forced > 0) {
+            const int64_t nt = ceil_div(n, BLOCK_N);
+            int s = (int)std::min<int64_t>(forced, nt);
+            while (s > 1 && ceil_div(nt, ceil_div(nt, s)) != s) --s;
+            return s;
+        }
+    }
     const int64_t n_mtiles = ceil_div(nq, BLOCK_M);
     const int64_t n_units = two_cta ? ceil_div(n_mtiles, 2) : n_mtiles;
     const int64_t workers = two_cta ? std::max(1, num_sms / 2) : num_sms;

@@ -44,8 +44,10 @@ class ShardedIndex:
         self.index = nv.Index(None, self.dtype, metric, self.device, on_device_ptr=local_rows.data_ptr(), n=n, d=d)
         self.d = d
 
-    def search(self, q, k: int):
+    def search(self, q, k: int, ids=None):
         """q: torch CUDA tensor [nq, d] (bf16 or fp32), replicated on every rank.
+        ids: optional GLOBAL row ids (ascending, replicated): each rank keeps those inside its row range — the sharded
+        form of FaissVS.__call__(ids=...) (faiss_vs.py:57-72).
         -> (scores [nq,k] float32, idx [nq,k] int64) CUDA tensors holding the GLOBAL top-k on every rank."""
         torch = self.torch
         assert q.is_cuda and q.is_contiguous() and q.shape[1] == self.d
@@ -54,8 +56,20 @@ class ShardedIndex:
         stream = torch.cuda.current_stream().cuda_stream
         loc_s = torch.empty((nq, k), dtype=torch.float32, device=q.device)
         loc_i = torch.empty((nq, k), dtype=torch.int64, device=q.device)
-        self.index.search_dev(q.data_ptr(), nq, k, q_dtype, loc_s.data_ptr(), loc_i.data_ptr(),
-                              id_offset=self.row_offset, stream=stream)
+        if ids is not None:
+            ids_t = torch.as_tensor(np.asarray(ids, dtype=np.int64), device=q.device)
+            mine = ids_t[(ids_t >= self.row_offset) & (ids_t < self.row_offset + self.index.n)] - self.row_offset
+            mine = mine.contiguous()
+            torch.cuda.current_stream().synchronize()
+            self.index.search_dev(q.data_ptr(), nq, k, q_dtype, loc_s.data_ptr(), loc_i.data_ptr(),
+                                  ids_ptr=mine.data_ptr() if mine.numel() else None, n_ids=int(mine.numel()), stream=stream)
+            if mine.numel() == 0:
+                loc_s.fill_(-3.4028234663852886e38 if self.metric == nv.METRIC_IP else 3.4028234663852886e38)
+                loc_i.fill_(-1)
+            loc_i = torch.where(loc_i >= 0, loc_i + self.row_offset, loc_i)
+        else:
+            self.index.search_dev(q.data_ptr(), nq, k, q_dtype, loc_s.data_ptr(), loc_i.data_ptr(),
+                                  id_offset=self.row_offset, stream=stream)
         if self.world == 1:
             return loc_s, loc_i
         all_s = torch.empty((self.world, nq, k), dtype=torch.float32, device=q.device)

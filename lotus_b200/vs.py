@@ -55,6 +55,17 @@ else:
             ...
 
 
+def _cuda_tensor(a: Any):
+    """The tensor itself when `a` is a torch CUDA tensor (device hand-off), else None."""
+    try:
+        import torch
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            return a
+    except ImportError:  # pragma: no cover
+        pass
+    return None
+
+
 def _to_host_matrix(a: Any, want_bf16: bool):
     """-> (array for the C-ABI, native dtype code, float32 view of the stored values)."""
     try:
@@ -107,6 +118,14 @@ class B200VS(VS):
     # -- index lifetime ---------------------------------------------------------------------------------------------
     def _build(self, embeddings: Any) -> nv.Index:
         nv.require_device()
+        t = _cuda_tensor(embeddings)
+        if t is not None and t.dim() == 2 and t.device.index == self.device:
+            # device hand-off: the encoder's output never visits the host on its way into the index
+            import torch
+            want = torch.bfloat16 if (self.dtype == "bf16" or (self.dtype == "auto" and t.dtype == torch.bfloat16)) else torch.float32
+            t = t.detach().to(want).contiguous()
+            return nv.Index(None, nv.BF16 if want == torch.bfloat16 else nv.F32, self.metric, self.device,
+                            on_device_ptr=t.data_ptr(), n=t.shape[0], d=t.shape[1])
         host, code, _ = _to_host_matrix(embeddings, self.dtype == "bf16")
         return nv.Index(host, code, self.metric, self.device)
 
@@ -171,10 +190,13 @@ class B200VS(VS):
         The reference's wrap-around of -1 to the last id when K > len(ids) (faiss_vs.py:71-72) is NOT reproduced."""
         if self.b2_index is None or self.index_dir is None:
             raise ValueError("Index not loaded")
+        ids_a = None if ids is None else np.asarray(list(ids) if not isinstance(ids, np.ndarray) else ids, dtype=np.int64)
+        t = _cuda_tensor(query_vectors)
+        if t is not None and ids_a is None and t.dim() == 2 and t.device.index == self.device:
+            return self._call_device(t, int(K))
         q, code, _ = _to_host_matrix(query_vectors, False)
         if q.shape[1] != self.b2_index.d:
             raise ValueError(f"query dimension {q.shape[1]} does not match the index dimension {self.b2_index.d}")
-        ids_a = None if ids is None else np.asarray(list(ids) if not isinstance(ids, np.ndarray) else ids, dtype=np.int64)
         try:
             distances, indices = self.b2_index.search(q, int(K), code, ids=ids_a)
         except nv.NativeError as e:
@@ -182,6 +204,26 @@ class B200VS(VS):
                 raise ValueError(e.msg) from e
             raise
         return RMOutput(distances=distances, indices=indices)
+
+    def _call_device(self, t: Any, K: int) -> RMOutput:
+        """Queries already on the GPU (e.g. straight out of the encoder): search in place, only the [Q,K] result travels."""
+        import torch
+        assert self.b2_index is not None
+        if t.shape[1] != self.b2_index.d:
+            raise ValueError(f"query dimension {t.shape[1]} does not match the index dimension {self.b2_index.d}")
+        q = t.detach()
+        q = q.contiguous() if q.dtype in (torch.float32, torch.bfloat16) else q.to(torch.float32).contiguous()
+        code = nv.BF16 if q.dtype == torch.bfloat16 else nv.F32
+        out_s = torch.empty((q.shape[0], K), dtype=torch.float32, device=q.device)
+        out_i = torch.empty((q.shape[0], K), dtype=torch.int64, device=q.device)
+        try:
+            self.b2_index.search_dev(q.data_ptr(), q.shape[0], K, code, out_s.data_ptr(), out_i.data_ptr(),
+                                     stream=torch.cuda.current_stream().cuda_stream)
+        except nv.NativeError as e:
+            if e.code in (nv.EINVAL, nv.ERANGE):
+                raise ValueError(e.msg) from e
+            raise
+        return RMOutput(distances=out_s.cpu().numpy(), indices=out_i.cpu().numpy())
 
     # -- extensions used by the re-registered operators --------------------------------------------------------------
     def threshold_pairs(self, threshold: float):

@@ -210,3 +210,31 @@ def test_kmeans_accumulate_and_sharded_driver_single_rank(gpu):
     a, c, obj = sharded_kmeans(idx, len(x), 0, 5, niter=4)
     assert np.array_equal(a, ao) and np.array_equal(bits(c), bits(co)) and np.allclose(obj, oo, rtol=1e-5)
     idx.close()
+
+
+def test_device_hand_off_and_sharded_ids_single_rank(env):
+    """torch CUDA tensors go into the index and the search without a host round trip; the sharded index
+    honours an ids subset."""
+    import torch
+    from lotus_b200.distributed import ShardedIndex
+    rm, vs, tmp = env
+    x = gauss(3000, 64, 90)
+    xt = torch.from_numpy(x).cuda()
+    vs.index(pd.Series(["d"] * 3000), xt, str(tmp / "dev"))
+    out = vs(xt[:7], 4)
+    Do, Io = oracle.knn(x, x[:7], 4)
+    assert np.array_equal(np.asarray(out.indices), Io) and np.array_equal(bits(out.distances), bits(Do))
+    xb = xt.to(torch.bfloat16)
+    vs_b = lotus.B200VS()
+    vs_b.index(None, xb, str(tmp / "devb"))
+    xbf = xb.float().cpu().numpy()
+    out = vs_b(xb[:7], 4)
+    Do, Io = oracle.knn(xbf, xbf[:7], 4)
+    assert np.array_equal(np.asarray(out.indices), Io) and np.array_equal(bits(out.distances), bits(Do))
+    vs_b.close()
+    sh = ShardedIndex(xt.contiguous(), 0)
+    ids = np.arange(5, 3000, 3)
+    s, i = sh.search(xt[:9].contiguous(), 6, ids=ids)
+    Ds, Is = oracle.knn_subset(x, x[:9], 6, ids)
+    assert np.array_equal(i.cpu().numpy(), Is) and np.array_equal(bits(s.cpu().numpy()), bits(Ds))
+    sh.close()
