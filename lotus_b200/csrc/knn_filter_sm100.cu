@@ -47,7 +47,10 @@ constexpr int PRODUCER_WARP = 4, MMA_WARP = 5, ALLOC_WARP = 6;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_LIMIT = 232448;  // 227 KB
 
-constexpr int PEND = 8;  // pending (not yet merged) candidates per query row and epilogue set between lockstep flushes
+// pending (not yet merged) candidates per query row and epilogue set: a flush is triggered once any row holds
+// PEND_FLUSH of them, checked after each 8-column group, so a row never holds more than PEND_FLUSH - 1 + 8 <= PEND
+constexpr int PEND = 16;
+constexpr int PEND_FLUSH = 8;
 __host__ __device__ constexpr int list_bytes(int kp) { return (kp + 2 * PEND) * BLOCK_M * 8; }
 __host__ __device__ constexpr int misc_bytes() { return 2 * BLOCK_N * 4 /*xnorm*/ + 256 /*barriers*/; }
 // cta_group::2 (a CTA pair computes 256 queries x 256 corpus rows): each CTA stages its own 128 query rows and HALF of
@@ -514,18 +517,32 @@ __device__ __forceinline__ void list_insert(float* sc, int32_t* id, float s, int
         minpos = -(pos + 1) - 1;
         return;  // threshold stays -inf
     }
-    float m = sc[0];
-    int mp = 0;
-#pragma unroll 8
-    for (int p = 1; p < KP; ++p) {
-        const float v = sc[p * BLOCK_M];
-        if (v < m) {
-            m = v;
-            mp = p;
+    // new minimum: four independent (value, position) chains so the shared-memory loads and compares overlap
+    static_assert(KP % 4 == 0, "list length must be a multiple of 4");
+    float m[4];
+    int mp[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        m[c] = sc[c * BLOCK_M];
+        mp[c] = c;
+    }
+#pragma unroll
+    for (int p = 4; p < KP; p += 4) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float v = sc[(p + c) * BLOCK_M];
+            if (v < m[c]) {
+                m[c] = v;
+                mp[c] = p + c;
+            }
         }
     }
-    thr = m;
-    minpos = mp;
+    // ties keep the lowest position, like the sequential scan
+    if (m[1] < m[0] || (m[1] == m[0] && mp[1] < mp[0])) { m[0] = m[1]; mp[0] = mp[1]; }
+    if (m[3] < m[2] || (m[3] == m[2] && mp[3] < mp[2])) { m[2] = m[3]; mp[2] = mp[3]; }
+    if (m[2] < m[0] || (m[2] == m[0] && mp[2] < mp[0])) { m[0] = m[2]; mp[0] = mp[2]; }
+    thr = m[0];
+    minpos = mp[0];
 }
 
 // Merge every lane's pending candidates into its list. Warp-collective: the loop bound is the warp-wide
@@ -547,15 +564,14 @@ __device__ __noinline__ float2 flush_pending(float* my_sc, int32_t* my_id, const
     return make_float2(thr, __int_as_float(minpos));
 }
 
-// One 32-row x 32-column block of scores (thread = row, v = its 32 scores). Two-level gating keeps the cost proportional
-// to the number of candidates: (1) one warp-wide OR reduction finds the 8-column groups in which ANY row beats its
-// threshold (late in a sweep almost none); (2) inside such a group one ballot per column, and only columns that hold a
-// candidate run the append (early in a sweep thresholds are low and most groups are "active", but most columns of most
-// rows are not). A row's pending buffer is flushed - by the whole warp, in lockstep - as soon as any row's is full, so
-// nothing is ever dropped.
+// One 32-row x 32-column block of scores (thread = row, v = its 32 scores). One warp-wide OR reduction finds the
+// 8-column groups in which ANY row beats its threshold (late in a sweep almost none); an active group runs 8 branch-free
+// predicated appends into the row's pending buffer and one vote. The pending buffers are merged into the lists by the
+// whole warp in lockstep (flush_pending) once any row holds PEND_FLUSH candidates, so nothing is ever dropped.
 template <int KPH, bool IS_L2>
 __device__ __forceinline__ void process_chunk32(float (&v)[32], int idx0, int valid, const float* xn, float* my_sc, int32_t* my_id,
-                                                float* pend_sc, int32_t* pend_id, float& thr, int& minpos, int& cnt) {
+                                                float* pend_sc, int32_t* pend_id, float& thr, int& minpos, int& cnt, bool dbg,
+                                                long long& dbg_flush, long long& dbg_cols) {
     if (valid <= 0) return;  // warp-uniform
     if constexpr (IS_L2) {
         const float4* xn4 = reinterpret_cast<const float4*>(xn);
@@ -586,22 +602,26 @@ __device__ __forceinline__ void process_chunk32(float (&v)[32], int idx0, int va
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         if (!(active & (1u << g))) continue;  // warp-uniform
+        // branch-free predicated appends for the 8 columns of an active group (cnt <= PEND_FLUSH - 1 on entry, so the
+        // pending buffer cannot overflow), then ONE vote per group decides whether the warp flushes
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
             const float s = v[8 * g + jj];
-            const bool cand = s > thr;
-            if (!__any_sync(0xffffffffu, cand)) continue;  // warp-uniform: no row wants this column
-            if (cand) {
+            if (s > thr) {
                 pend_sc[cnt * BLOCK_M] = s;
                 pend_id[cnt * BLOCK_M] = idx0 + 8 * g + jj;
                 ++cnt;
             }
-            if (__any_sync(0xffffffffu, cnt >= PEND)) {
-                const float2 fr = flush_pending<KPH>(my_sc, my_id, pend_sc, pend_id, cnt, thr, minpos);
-                thr = fr.x;
-                minpos = __float_as_int(fr.y);
-                cnt = 0;
-            }
+        }
+        if (dbg) dbg_cols += 1;
+        if (__any_sync(0xffffffffu, cnt >= PEND_FLUSH)) {
+            long long f0 = 0;
+            if (dbg) f0 = clock64();
+            const float2 fr = flush_pending<KPH>(my_sc, my_id, pend_sc, pend_id, cnt, thr, minpos);
+            thr = fr.x;
+            minpos = __float_as_int(fr.y);
+            cnt = 0;
+            if (dbg) dbg_flush += clock64() - f0;
         }
     }
 }
@@ -648,7 +668,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         float* xn_tile = s_xn + e * BLOCK_N;
         uint32_t my_phase = 0;   // parity of the next completion of tmem_full[e]
         uint32_t tile_ctr = 0;   // tiles issued by the MMA warp so far; stage = tile_ctr & 1
-        long long epi_wait = 0;
+        long long epi_wait = 0, dbg_flush = 0, dbg_cols = 0;
         const long long epi_begin = p.debug_mode == 2 ? clock64() : 0;
         for (int item = sc.worker; item < n_items; item += sc.n_workers) {
             int m_tile, split, t0, t1;
@@ -692,7 +712,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     tmem_ld32(taddr + (2 * h + 1) * 32, vb);   // chunk 2h+1 in flight while va is processed
                     if (p.debug_mode != 1)
                         process_chunk32<KPH, IS_L2>(va, col0 + (2 * h) * 32, ncols - (2 * h) * 32, xn_tile + (2 * h) * 32, my_sc, my_id,
-                                                    pend_sc, pend_id, thr, minpos, cnt);
+                                                    pend_sc, pend_id, thr, minpos, cnt, p.debug_mode == 2, dbg_flush, dbg_cols);
                     tmem_ld_wait();                            // chunk 2h+1 is in vb
                     if (h < 3) {
                         tmem_ld32(taddr + (2 * h + 2) * 32, va);  // next chunk in flight while vb is processed
@@ -707,7 +727,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     }
                     if (p.debug_mode != 1)
                         process_chunk32<KPH, IS_L2>(vb, col0 + (2 * h + 1) * 32, ncols - (2 * h + 1) * 32, xn_tile + (2 * h + 1) * 32, my_sc,
-                                                    my_id, pend_sc, pend_id, thr, minpos, cnt);
+                                                    my_id, pend_sc, pend_id, thr, minpos, cnt, p.debug_mode == 2, dbg_flush, dbg_cols);
                     else if (vb[0] == 12345.678f) thr = va[1] + vb[1];  // keep the loads alive in the timing experiment
                 }
             }
@@ -737,6 +757,8 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             atomicAdd(&p.dbg[4], (unsigned long long)(clock64() - epi_begin));
             atomicAdd(&p.dbg[5], (unsigned long long)epi_wait);
             atomicAdd(&p.dbg[6], 1ull);
+            atomicAdd(&p.dbg[7], (unsigned long long)dbg_flush);
+            atomicAdd(&p.dbg[8], (unsigned long long)dbg_cols);
         }
     }
 
@@ -956,23 +978,21 @@ int filter_choose_splits(int64_t nq, int64_t n, int num_sms, bool two_cta) {
     const int64_t n_units = two_cta ? ceil_div(n_mtiles, 2) : n_mtiles;
     const int64_t workers = two_cta ? std::max(1, num_sms / 2) : num_sms;
     const int64_t n_ntiles = ceil_div(n, BLOCK_N);
+    // cost model (measured, profiles/README.md): an item costs its corpus tiles plus ~13 tile-times of list warm-up, the
+    // kernel takes `waves` such items back to back, and every extra split adds two candidate lists per query to finalize
+    constexpr double kWarmupTiles = 13.0;
     int best = 1;
-    double best_eff = -1.0;
+    double best_cost = 1e300;
     for (int s = 1; s <= 256 && s <= n_ntiles; ++s) {
         const int64_t tps = ceil_div(n_ntiles, s);
-        const int64_t s_eff = ceil_div(n_ntiles, tps);  // splits that actually receive tiles
-        if (s_eff != s) continue;
+        if (ceil_div(n_ntiles, tps) != s) continue;  // every split must receive tiles
         const int64_t items = n_units * s;
         const int64_t waves = ceil_div(items, workers);
-        double eff = (double)items / (double)(waves * workers);
-        // each split restarts its candidate lists and adds finalize work: prefer fewer, longer splits
-        if (tps < 4 && s > 1) eff -= 0.25;
-        eff -= 0.002 * s;
-        if (eff > best_eff + 1e-9) {
-            best_eff = eff;
+        const double cost = (double)waves * ((double)tps + kWarmupTiles) * (1.0 + 0.004 * s);
+        if (cost < best_cost - 1e-9) {
+            best_cost = cost;
             best = s;
         }
-        if (items >= 8 * workers && eff > 0.93) break;
     }
     return best;
 }
@@ -1051,9 +1071,9 @@ int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int
         const double nm = h[3] ? (double)h[3] : 1.0, ne = h[6] ? (double)h[6] : 1.0;
         fprintf(stderr,
                 "[b2 filter dbg] mma warps=%llu: total %.3e cyc, wait_full %.1f%%, wait_tmem_empty %.1f%% | epilogue warps=%llu: total "
-                "%.3e cyc, wait_tmem_full %.1f%%\n",
+                "%.3e cyc, wait_tmem_full %.1f%%, in flush %.1f%%, active columns/warp %.3e\n",
                 h[3], h[0] / nm, 100.0 * h[1] / (double)(h[0] ? h[0] : 1), 100.0 * h[2] / (double)(h[0] ? h[0] : 1), h[6], h[4] / ne,
-                100.0 * h[5] / (double)(h[4] ? h[4] : 1));
+                100.0 * h[5] / (double)(h[4] ? h[4] : 1), 100.0 * h[7] / (double)(h[4] ? h[4] : 1), h[8] / ne);
     }
     return rc;
 }
