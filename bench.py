@@ -284,8 +284,16 @@ def main() -> None:
     peak_tf, peak_src = load_peaks()
     flops_launch = 2.0 * nq * (hi - lo) * d  # algorithmic: 2*N_local*d per query
     achieved_tf = flops_launch / (kernel_ms * 1e-3) / 1e12 if kernel_ms == kernel_ms and kernel_ms > 0 else None
+    traffic = None
+    try:  # DRAM bytes of one launch of this kernel on this shape, from the committed `ncu --set full` capture
+        with open(os.path.join(ROOT, "profiles", "filter_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("nq") == nq and tj.get("n_local") == hi - lo and tj.get("d") == d:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    except Exception:
+        traffic = None
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": None,
+                "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": traffic,
                 "kernel": "knn_filter_kernel<KP=64,IP,bf16,cta_group::2>", "kernel_ms": kernel_ms, "peak_source": peak_src,
                 "algorithmic_flops_per_launch": flops_launch,
                 "hbm_floor_ms": ((hi - lo) * d * 2 + nq * d * 2 + nq * k * 12) / 6.4843e12 * 1e3}

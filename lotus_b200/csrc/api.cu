@@ -93,7 +93,11 @@ int search_core(b2_index* idx, const MatView& X, int metric, const void* q_dev, 
     }
     const int kp = filter_kp_for_k(k);
     const bool use_filter = kp != 0 && X.n >= 512;
-    const int64_t dense_rows_cap = std::max<int64_t>(1, (int64_t)(256ull << 20) / (X.n * 4));
+    int64_t npow2 = 1;
+    while (npow2 < X.n) npow2 <<= 1;
+    const bool full_sort = k > dense_select_max_k();  // dense path sorts whole rows: 12 bytes of workspace per padded column
+    const int64_t dense_rows_cap =
+        std::max<int64_t>(1, (int64_t)(256ull << 20) / (full_sort ? npow2 * 12 : X.n * 4));
     if (!use_filter) {
         if (k > dense_max_k()) {
             set_error("k=%d is not supported (max %d)", k, dense_max_k());
@@ -101,8 +105,9 @@ int search_core(b2_index* idx, const MatView& X, int metric, const void* q_dev, 
         }
         const int64_t rows = std::min<int64_t>(dense_rows_cap, nq);
         B2_TRY(idx->dense.ensure((size_t)rows * X.n * sizeof(float)));
+        if (full_sort) B2_TRY(idx->sort_keys.ensure((size_t)rows * npow2 * sizeof(uint64_t)));
         B2_TRY(launch_dense_topk(X, q_dev, q_dtype, nq, nullptr, nq, metric, k, id_map, id_offset, idx->dense.as<float>(), rows,
-                                 out_sc, out_id, st));
+                                 full_sort ? idx->sort_keys.as<uint64_t>() : nullptr, out_sc, out_id, st));
         g_stats[ST_FALLBACK] += nq;
         return B2_OK;
     }
@@ -162,7 +167,7 @@ int search_core(b2_index* idx, const MatView& X, int metric, const void* q_dev, 
             const int64_t rows = std::min<int64_t>(dense_rows_cap, (int64_t)sel.size());
             B2_TRY(idx->dense.ensure((size_t)rows * X.n * sizeof(float)));
             B2_TRY(launch_dense_topk(X, qc, q_dtype, nqc, idx->sel.as<int32_t>(), (int64_t)sel.size(), metric, k, id_map,
-                                     id_offset, idx->dense.as<float>(), rows, osc, oid, st));
+                                     id_offset, idx->dense.as<float>(), rows, nullptr, osc, oid, st));
             B2_CUDA(cudaStreamSynchronize(st));  // `sel` (host vector) must outlive the copy
         }
     }
@@ -266,7 +271,7 @@ void b2_index_free(b2_index* idx) {
     DeviceGuard guard(idx->device);
     DevBuf* bufs[] = {&idx->store, &idx->filt_pad, &idx->norm2, &idx->scalar, &idx->q_in, &idx->q_filt, &idx->cand_score,
                       &idx->cand_id, &idx->cand_thr, &idx->flags, &idx->sel, &idx->dense, &idx->out_sc, &idx->out_id,
-                      &idx->ids_dev, &idx->sub_store, &idx->sub_filt, &idx->sub_norm2};
+                      &idx->ids_dev, &idx->sub_store, &idx->sub_filt, &idx->sub_norm2, &idx->sort_keys};
     for (DevBuf* b : bufs) b->release();
     idx->h_flags.release();
     if (idx->ev0) cudaEventDestroy(idx->ev0);

@@ -121,9 +121,10 @@ int launch_finalize(const MatView& X, const void* q, int q_dtype, int64_t nq, in
                     int32_t* flags, cudaStream_t stream);
 int launch_dense_topk(const MatView& X, const void* q, int q_dtype, int64_t nq, const int32_t* q_sel,
                       int64_t n_sel, int metric, int k, const int64_t* id_map, int64_t id_offset, float* dense_ws,
-                      int64_t dense_ws_rows, float* out_scores, int64_t* out_idx, cudaStream_t stream);
+                      int64_t dense_ws_rows, uint64_t* sort_ws, float* out_scores, int64_t* out_idx, cudaStream_t stream);
 int launch_merge_topk(const float* scores, const int64_t* idx, int g, int64_t nq, int k, int metric,
                       float* out_scores, int64_t* out_idx, cudaStream_t stream);
-int dense_max_k();
+int dense_max_k();         // largest k any path supports
+int dense_select_max_k();  // largest k of the radix-select path (beyond it: full row sort)
 
 }  // namespace b2

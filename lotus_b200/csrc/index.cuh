@@ -85,7 +85,7 @@ struct b2_index {
     MatView view;
     // per-call workspaces
     DevBuf q_in, q_filt, cand_score, cand_id, cand_thr, flags, sel, dense, out_sc, out_id, ids_dev;
-    DevBuf sub_store, sub_filt, sub_norm2;
+    DevBuf sub_store, sub_filt, sub_norm2, sort_keys;
     HostBuf h_flags;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

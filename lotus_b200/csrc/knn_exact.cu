@@ -602,6 +602,58 @@ dense_select_kernel(const float* scores, int64_t n, const int32_t* q_sel, int me
     }
 }
 
+// ---- large k (> SEL_MAX_K): full sort of a dense score row ------------------------------------------------------------
+// One CTA per selected query: bitonic sort of (best-first key, tie order) over the whole row in global memory, then the
+// first k entries. faiss switches to a reservoir for k >= 100 whose tie retention at the cut is unspecified; sorted
+// truncation with the heap's order ((score desc, id desc) for IP, (dist asc, id asc) for L2) is used here. This is the
+// path of the cascade callers that ask for K = len(df) (lotus/sem_ops/sem_filter.py:486-497, sem_join.py:343-373).
+constexpr int SORT_THREADS = 1024;
+__global__ void __launch_bounds__(SORT_THREADS)
+dense_sort_kernel(const float* scores, int64_t n, int64_t npow, uint64_t* keys, const int32_t* q_sel, int metric, int k,
+                  const int64_t* id_map, int64_t id_offset, float* out_scores, int64_t* out_idx) {
+    const int s = blockIdx.x;
+    const int64_t qo = q_sel ? q_sel[s] : s;
+    const float* row = scores + (size_t)s * n;
+    uint64_t* kr = keys + (size_t)s * npow;
+    const bool is_l2 = metric == B2_METRIC_L2;
+    for (int64_t j = threadIdx.x; j < npow; j += SORT_THREADS) {
+        uint64_t kk = KEY_WORST;
+        if (j < n) kk = ((uint64_t)best_first_key(row[j], metric) << 32) | (is_l2 ? (uint32_t)j : ~(uint32_t)j);
+        kr[j] = kk;
+    }
+    __syncthreads();
+    for (int64_t kk = 2; kk <= npow; kk <<= 1) {
+        for (int64_t j = kk >> 1; j > 0; j >>= 1) {
+            for (int64_t i = threadIdx.x; i < npow; i += SORT_THREADS) {
+                const int64_t ixj = i ^ j;
+                if (ixj > i) {
+                    const bool up = (i & kk) == 0;
+                    const uint64_t a = kr[i], b = kr[ixj];
+                    if ((a > b) == up) {
+                        kr[i] = b;
+                        kr[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const float pad = is_l2 ? FLT_MAX : -FLT_MAX;
+    for (int64_t o = threadIdx.x; o < k; o += SORT_THREADS) {
+        float sc = pad;
+        int64_t oid = -1;
+        if (o < n) {
+            const uint64_t e = kr[o];
+            const uint32_t lo = (uint32_t)(e & 0xffffffffu);
+            const int64_t id = (int64_t)(is_l2 ? lo : ~lo);
+            sc = best_first_unkey((uint32_t)(e >> 32), metric);
+            oid = id_map ? id_map[id] : id + id_offset;
+        }
+        out_scores[(size_t)qo * k + o] = sc;
+        out_idx[(size_t)qo * k + o] = oid;
+    }
+}
+
 // ---- k-way merge of per-shard lists -----------------------------------------------------------------------------
 template <int R>
 __global__ void __launch_bounds__(128) merge_topk_kernel(const float* scores, const int64_t* idx, int g, int64_t nq, int k,
@@ -658,7 +710,8 @@ int grid_for(int64_t work_items, int threads, int cap = 148 * 16) {
 
 }  // namespace
 
-int dense_max_k() { return SEL_MAX_K; }
+int dense_max_k() { return 1 << 24; }
+int dense_select_max_k() { return SEL_MAX_K; }
 
 int launch_prep_queries(const void* q, int q_dtype, int64_t nq, int d, void* q_filt, int filt_dtype,
                         int64_t filt_pitch, cudaStream_t stream) {
@@ -748,13 +801,16 @@ int launch_finalize(const MatView& X, const void* q, int q_dtype, int64_t nq, in
 
 int launch_dense_topk(const MatView& X, const void* q, int q_dtype, int64_t nq, const int32_t* q_sel, int64_t n_sel,
                       int metric, int k, const int64_t* id_map, int64_t id_offset, float* dense_ws,
-                      int64_t dense_ws_rows, float* out_scores, int64_t* out_idx, cudaStream_t stream) {
+                      int64_t dense_ws_rows, uint64_t* sort_ws, float* out_scores, int64_t* out_idx, cudaStream_t stream) {
     (void)nq;
     if (n_sel <= 0) return B2_OK;
-    if (k > SEL_MAX_K) {
-        set_error("k=%d exceeds the dense path's limit %d", k, SEL_MAX_K);
-        return B2_ERANGE;
+    const bool full_sort = k > SEL_MAX_K;  // needs sort_ws[dense_ws_rows, next_pow2(n)]
+    if (full_sort && !sort_ws) {
+        set_error("internal: k=%d needs the sort workspace", k);
+        return B2_EINVAL;
     }
+    int64_t npow = 1;
+    while (npow < X.n) npow <<= 1;
     const int d4 = ((X.d + 3) >> 2) << 2;
     const size_t smem = (size_t)8 * d4 * 4;
     if (smem > 48 * 1024) {
@@ -776,7 +832,10 @@ int launch_dense_topk(const MatView& X, const void* q, int q_dtype, int64_t nq, 
         }
         float* os = q_sel ? out_scores : out_scores + (size_t)s0 * k;
         int64_t* oi = q_sel ? out_idx : out_idx + (size_t)s0 * k;
-        dense_select_kernel<<<sc, SEL_THREADS, 0, stream>>>(dense_ws, X.n, sel, metric, k, id_map, id_offset, os, oi);
+        if (full_sort)
+            dense_sort_kernel<<<sc, SORT_THREADS, 0, stream>>>(dense_ws, X.n, npow, sort_ws, sel, metric, k, id_map, id_offset, os, oi);
+        else
+            dense_select_kernel<<<sc, SEL_THREADS, 0, stream>>>(dense_ws, X.n, sel, metric, k, id_map, id_offset, os, oi);
         B2_LAUNCH_CHECK();
     }
     return B2_OK;

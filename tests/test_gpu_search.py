@@ -117,7 +117,7 @@ def test_edge_shapes(gpu):
     with pytest.raises(gpu.NativeError):
         idx.search(q, 0)
     with pytest.raises(gpu.NativeError):
-        idx.search(q, gpu.lib().b2_max_k() + 1)
+        idx.search(q[:1], gpu.lib().b2_max_k() + 1)
     idx.close()
     empty = gpu.Index(np.zeros((0, 32), np.float32), gpu.F32, 1)
     D, I = empty.search(q, 2)
@@ -185,3 +185,22 @@ def test_filter_error_stays_inside_the_certified_margin(gpu):
     for dtype in ("f32", "bf16"):
         check(gpu, x.astype(np.float32), q.astype(np.float32), 4, 0, dtype, expect_filter=True)
         check(gpu, x.astype(np.float32), q.astype(np.float32), 4, 1, dtype, expect_filter=True)
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_large_k_full_sort_path(gpu, metric):
+    """k beyond the radix-select limit (the cascade callers' K = len(df)): whole-row sort in faiss heap order."""
+    x, q = gauss(5000, 48, 30), gauss(6, 48, 31)
+    x[17] = x[4000]  # an exact duplicate pair: tie order must follow the heap convention
+    idx = gpu.Index(x, gpu.F32, metric)
+    S = oracle.scores(x, q, metric)
+    for k in (3000, 5000, 6000):
+        D, I = idx.search(q, k)
+        for r in range(len(q)):
+            ids = np.arange(5000)
+            order = np.lexsort((-ids, -S[r].astype(np.float64))) if metric == 0 else np.lexsort((ids, S[r].astype(np.float64)))
+            m = min(k, 5000)
+            assert np.array_equal(I[r, :m], order[:m])
+            assert np.array_equal(bits(D[r, :m]), bits(S[r][order[:m]]))
+            assert (I[r, m:] == -1).all() and (D[r, m:] == (-FMAX if metric == 0 else FMAX)).all()
+    idx.close()
