@@ -260,6 +260,12 @@ def main() -> None:
     launches_per_step = st["launches"] / max(args.steps, 1) + (2 if world > 1 else 0)  # + all-gather kernels are NCCL's
     fallback_q = st["fallback_queries"]
     kernel_ms = float(np.mean(filt_ms)) if filt_ms else float("nan")
+    kernel_ms_ranks = [kernel_ms]
+    if world > 1:  # the all-gather makes every step wait for the slowest rank: report the spread
+        t = torch.tensor([kernel_ms], device=device, dtype=torch.float64)
+        allk = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allk, t)
+        kernel_ms_ranks = [float(a.item()) for a in allk]
 
     # ---- end to end: host (pinned) queries in, host results out, every step ------------------------------------------
     q_host = queries.cpu().pin_memory()
@@ -295,6 +301,7 @@ def main() -> None:
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": traffic,
                 "kernel": "knn_filter_kernel<KP=64,IP,bf16,cta_group::2>", "kernel_ms": kernel_ms, "peak_source": peak_src,
+                "kernel_ms_per_rank": [round(k, 3) for k in kernel_ms_ranks],
                 "algorithmic_flops_per_launch": flops_launch,
                 "hbm_floor_ms": ((hi - lo) * d * 2 + nq * d * 2 + nq * k * 12) / 6.4843e12 * 1e3}
 
