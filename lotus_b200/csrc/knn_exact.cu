@@ -289,56 +289,29 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(const Finalize
     }
     __syncwarp();
 
-    // 3. canonical re-scoring of the surviving candidates. Eight rows are walked together so that each lane has eight
-    //    independent row loads in flight per step (the gather is latency-bound otherwise); the accumulation order per
-    //    row is unchanged (lane-strided groups in increasing index), so the score stays the canonical one.
-    constexpr int U = 8;
-    const int ngroups = (p.d + 3) >> 2;
-    for (int c0 = 0; c0 < NC; c0 += U) {
-        int32_t ids[U];
-        const char* rows[U];
+    // 3. canonical re-scoring of the surviving candidates, four rows per step (survivors are sorted by filter score,
+    //    so the pruned tail of the list is skipped as soon as a whole step is empty)
+    for (int c0 = 0; c0 < NC; c0 += 4) {
+        double part[4];
+        int32_t ids[4];
         bool any_valid = false;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
+        for (int u = 0; u < 4; ++u) {
             ids[u] = s_id[c0 + u];
             any_valid |= ids[u] >= 0;
         }
-        if (!any_valid) {  // survivors are sorted by filter score: the rest of the list was pruned
+        if (!any_valid) break;
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (lane == 0) s_ex[c0 + u] = 0.f;
-            continue;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            rows[u] = reinterpret_cast<const char*>(p.store) + (size_t)(ids[u] >= 0 ? ids[u] : 0) * p.d * esz;
-        double part[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) part[u] = 0.0;
-        for (int g = lane; g < ngroups; g += 32) {
-            float x[U][4];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (ids[u] >= 0) load_group(rows[u], p.dtype, g, p.d, vec, x[u]);
-                else x[u][0] = x[u][1] = x[u][2] = x[u][3] = 0.f;
-            }
-            const float4 q4 = *reinterpret_cast<const float4*>(q_s + 4 * g);
-            const float qq[4] = {q4.x, q4.y, q4.z, q4.w};
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    if (is_l2) {
-                        const double diff = (double)qq[e] - (double)x[u][e];
-                        part[u] = fma(diff, diff, part[u]);
-                    } else {
-                        part[u] = fma((double)qq[e], (double)x[u][e], part[u]);
-                    }
-                }
+        for (int u = 0; u < 4; ++u) {
+            part[u] = 0.0;
+            if (ids[u] >= 0) {
+                const char* row = reinterpret_cast<const char*>(p.store) + (size_t)ids[u] * p.d * esz;
+                part[u] = is_l2 ? canonical_partial<true>(q_s, row, p.dtype, p.d, vec, lane)
+                                : canonical_partial<false>(q_s, row, p.dtype, p.d, vec, lane);
             }
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
+        for (int u = 0; u < 4; ++u) {
             const double tot = butterfly_sum(part[u]);
             if (lane == 0) s_ex[c0 + u] = (float)tot;
         }
