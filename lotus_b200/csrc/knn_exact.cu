@@ -185,6 +185,53 @@ __global__ void gather_rows_kernel(const char* x, size_t row_bytes, const int64_
     }
 }
 
+// Canonical partials of U rows at once (vectorisable rows only): the U independent row loads of a step are issued
+// back to back, so each lane keeps U gathers in flight. Per row the accumulation order is exactly canonical_partial's.
+template <bool IS_L2, bool BF16, int U>
+__device__ __forceinline__ void canonical_partial_multi(const float* q_s, const char* const (&rows)[U], int d, int lane,
+                                                        double (&acc)[U]) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u] = 0.0;
+    const int ngroups = d >> 2;
+    for (int g = lane; g < ngroups; g += 32) {
+        float x[U][4];
+        if constexpr (BF16) {
+            uint2 t[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) t[u] = __ldg(reinterpret_cast<const uint2*>(rows[u]) + g);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                x[u][0] = __uint_as_float(t[u].x << 16);
+                x[u][1] = __uint_as_float(t[u].x & 0xffff0000u);
+                x[u][2] = __uint_as_float(t[u].y << 16);
+                x[u][3] = __uint_as_float(t[u].y & 0xffff0000u);
+            }
+        } else {
+            float4 t[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) t[u] = __ldg(reinterpret_cast<const float4*>(rows[u]) + g);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                x[u][0] = t[u].x; x[u][1] = t[u].y; x[u][2] = t[u].z; x[u][3] = t[u].w;
+            }
+        }
+        const float4 q4 = *reinterpret_cast<const float4*>(q_s + 4 * g);
+        const float qq[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (IS_L2) {
+                    const double diff = (double)qq[e] - (double)x[u][e];
+                    acc[u] = fma(diff, diff, acc[u]);
+                } else {
+                    acc[u] = fma((double)qq[e], (double)x[u][e], acc[u]);
+                }
+            }
+        }
+    }
+}
+
 // ---- finalize ------------------------------------------------------------------------------------------------
 struct FinalizeParams {
     const void* store;
@@ -301,13 +348,28 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(const Finalize
             any_valid |= ids[u] >= 0;
         }
         if (!any_valid) break;
+        if (vec) {
+            // interleaved gather of the four rows (an invalid slot re-reads the first row of the step: a cache hit)
+            const char* rows[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            part[u] = 0.0;
-            if (ids[u] >= 0) {
-                const char* row = reinterpret_cast<const char*>(p.store) + (size_t)ids[u] * p.d * esz;
-                part[u] = is_l2 ? canonical_partial<true>(q_s, row, p.dtype, p.d, vec, lane)
-                                : canonical_partial<false>(q_s, row, p.dtype, p.d, vec, lane);
+            for (int u = 0; u < 4; ++u)
+                rows[u] = reinterpret_cast<const char*>(p.store) + (size_t)(ids[u] >= 0 ? ids[u] : ids[0]) * p.d * esz;
+            if (p.dtype == B2_BF16) {
+                if (is_l2) canonical_partial_multi<true, true, 4>(q_s, rows, p.d, lane, part);
+                else canonical_partial_multi<false, true, 4>(q_s, rows, p.d, lane, part);
+            } else {
+                if (is_l2) canonical_partial_multi<true, false, 4>(q_s, rows, p.d, lane, part);
+                else canonical_partial_multi<false, false, 4>(q_s, rows, p.d, lane, part);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                part[u] = 0.0;
+                if (ids[u] >= 0) {
+                    const char* row = reinterpret_cast<const char*>(p.store) + (size_t)ids[u] * p.d * esz;
+                    part[u] = is_l2 ? canonical_partial<true>(q_s, row, p.dtype, p.d, vec, lane)
+                                    : canonical_partial<false>(q_s, row, p.dtype, p.d, vec, lane);
+                }
             }
         }
 #pragma unroll

@@ -8,6 +8,7 @@ it: per-shard flat search, then a merge by (score, shard order). It equals the s
 exact fp32 tie straddles rank K across shards."""
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import numpy as np
@@ -72,14 +73,25 @@ class ShardedIndex:
                                   id_offset=self.row_offset, stream=stream)
         if self.world == 1:
             return loc_s, loc_i
+        timing = os.environ.get("B2_SHARD_TIMING") == "1"
+        if timing:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
         all_s = torch.empty((self.world, nq, k), dtype=torch.float32, device=q.device)
         all_i = torch.empty((self.world, nq, k), dtype=torch.int64, device=q.device)
         self.dist.all_gather_into_tensor(all_s, loc_s, group=self.group)
         self.dist.all_gather_into_tensor(all_i, loc_i, group=self.group)
+        if timing:
+            ev[1].record()
         out_s = torch.empty_like(loc_s)
         out_i = torch.empty_like(loc_i)
         nv.merge_topk_dev(all_s.data_ptr(), all_i.data_ptr(), self.world, nq, k, self.metric, self.device,
                           out_s.data_ptr(), out_i.data_ptr(), stream=stream)
+        if timing:
+            ev[2].record()
+            torch.cuda.synchronize()
+            self.last_phase_ms = {"filter": self.index.last_filter_ms(), "all_gather(+wait for slowest rank)": ev[0].elapsed_time(ev[1]),
+                                  "merge": ev[1].elapsed_time(ev[2])}
         return out_s, out_i
 
     def last_filter_ms(self) -> float:
