@@ -57,3 +57,32 @@ class NumpyVS:
         else:
             D, I = oracle.knn_subset(self.x, q, K, np.asarray(list(ids), dtype=np.int64), self.metric)
         return RMOutput(distances=D, indices=I)
+
+    # extension methods the re-registered accessors use (oracle-backed, tests only)
+    def threshold_pairs(self, threshold):
+        import oracle
+        pi, pj, _ = oracle.threshold_pairs(self.x, float(threshold))
+        return pi, pj
+
+    def kmeans(self, ids, ncentroids, niter=20, seed=1234, full_lloyd=False):
+        import oracle
+        return oracle.kmeans(self.x[np.asarray(ids, dtype=np.int64)], ncentroids, niter=niter, seed=seed, full_lloyd=full_lloyd)
+
+
+def frame_from_json(j):
+    import pandas as pd
+    return pd.DataFrame(j["data"], columns=j["columns"], index=j["index"])
+
+
+def assert_frame_matches_json(df, j):
+    """DataFrame equals a fixture produced by the reference's operator code (tests/golden/reference_ops.json)."""
+    assert [str(c) for c in df.columns] == j["columns"]
+    assert [int(i) for i in df.index] == j["index"]
+    got = df.to_numpy().tolist()
+    assert len(got) == len(j["data"])
+    for r_got, r_want in zip(got, j["data"]):
+        for a, b in zip(r_got, r_want):
+            if isinstance(b, float):
+                assert np.float32(a) == np.float32(b), (a, b)
+            else:
+                assert a == b, (a, b)

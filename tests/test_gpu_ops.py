@@ -238,3 +238,14 @@ def test_device_hand_off_and_sharded_ids_single_rank(env):
     Ds, Is = oracle.knn_subset(x, x[:9], 6, ids)
     assert np.array_equal(i.cpu().numpy(), Is) and np.array_equal(bits(s.cpu().numpy()), bits(Ds))
     sh.close()
+
+
+def test_reference_operator_frames_on_gpu(env):
+    """The frames the REFERENCE's operator code produced (tests/golden/reference_ops.json) are reproduced with B200VS."""
+    import test_reference_golden as trg
+    rm, vs, tmp = env
+    lotus.settings.configure(rm=lotus.HashRM(dim=trg.GOLD["sim_join"]["dim"]))
+    trg.replay_sim_join(tmp)
+    trg.replay_search(tmp)
+    trg.replay_dedup(tmp)
+    trg.replay_cluster(tmp)
