@@ -230,7 +230,8 @@ int assign_points(b2_index* idx, const void* pts, int64_t m, const float* cent, 
 int update_centroids(b2_index* idx, const void* x, const int64_t* row_ids, int64_t n, const int64_t* assign, int k, KmWork& w,
                      float* cent, cudaStream_t st, int normalize = 1) {
     const int d = idx->d;
-    int64_t nb = std::min<int64_t>(4096, std::max<int64_t>(1, ceil_div(n, 256)));
+    // one warp per block walks its point range in order; 1024 ranges keep the per-centroid scan over blocks short
+    int64_t nb = std::min<int64_t>(1024, std::max<int64_t>(1, ceil_div(n, 256)));
     while (nb > 1 && nb * (int64_t)k > ((int64_t)1 << 26)) nb /= 2;
     const int64_t L = ceil_div(n, nb);
     nb = ceil_div(n, L);
