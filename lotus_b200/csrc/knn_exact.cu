@@ -112,6 +112,59 @@ __device__ __forceinline__ void warp_bitonic_sort(uint64_t (&key)[R], int lane) 
     }
 }
 
+// Sorts a BITONIC sequence of 32*R keys ascending (the merge half of the network: log2(32R) stages instead of the
+// full sort's log^2).
+template <int R>
+__device__ __forceinline__ void warp_bitonic_merge(uint64_t (&key)[R], int lane) {
+#pragma unroll
+    for (int j = 16 * R; j > 0; j >>= 1) {
+        if (j >= 32) {
+            const int jr = j >> 5;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int rp = r ^ jr;
+                if (rp > r) {
+                    const uint64_t a = key[r], b = key[rp];
+                    key[r] = a < b ? a : b;
+                    key[rp] = a < b ? b : a;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint64_t other = __shfl_xor_sync(FULL, key[r], j);
+                const bool lower = ((lane & j) == 0);
+                const uint64_t mn = key[r] < other ? key[r] : other;
+                const uint64_t mx = key[r] < other ? other : key[r];
+                key[r] = lower ? mn : mx;
+            }
+        }
+    }
+}
+
+// buf (sorted ascending, 32*R keys) <- the 32*R smallest of buf U chunk (chunk sorted ascending), sorted again.
+// Returns the smallest key that was dropped (KEY_WORST if none): min(buf[e], chunk[N-1-e]) keeps exactly the lower half
+// of the union and is bitonic, so one merge pass re-sorts it.
+template <int R>
+__device__ __forceinline__ uint64_t warp_merge_keep_low(uint64_t (&buf)[R], const uint64_t (&chunk)[R], int lane) {
+    uint64_t best_drop = KEY_WORST;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint64_t rev = __shfl_sync(FULL, chunk[R - 1 - r], 31 - lane);  // chunk[N-1-e] for e = r*32 + lane
+        const uint64_t a = buf[r];
+        const uint64_t hi = a < rev ? rev : a;
+        buf[r] = a < rev ? a : rev;
+        best_drop = hi < best_drop ? hi : best_drop;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const uint64_t o = __shfl_xor_sync(FULL, best_drop, off);
+        best_drop = o < best_drop ? o : best_drop;
+    }
+    warp_bitonic_merge<R>(buf, lane);
+    return best_drop;
+}
+
 // ---- small utility kernels -------------------------------------------------------------------------------------
 __global__ void prep_queries_kernel(const void* q, int q_dtype, int64_t nq, int d, void* out, int out_dtype, int64_t pitch) {
     const int64_t total = nq * pitch;
@@ -281,38 +334,44 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(const Finalize
     }
     const double qn2 = butterfly_sum(qacc);
 
-    // 2. merge the per-split candidate lists by filter score (larger is better for both metrics)
-    uint64_t keys[2 * R];
-#pragma unroll
-    for (int r = 0; r < 2 * R; ++r) keys[r] = KEY_WORST;
+    // 2. merge the candidate lists by filter score (larger is better for both metrics): chunks of 32*R keys (as many
+    //    whole lists as fit) are sorted with the bitonic network and folded into the running best 32*R with one
+    //    compare-with-reversed + bitonic-merge pass each (instead of re-sorting 2*32*R keys per list)
+    uint64_t keys[R];
     float bound = -INFINITY;
-    for (int s = 0; s < p.n_splits; ++s) {
-        const size_t lbase = ((size_t)q * p.n_splits + s) * p.list_len;
-        bound = fmaxf(bound, p.cand_thr[(size_t)q * p.n_splits + s]);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int e = r * 32 + lane;
-            uint64_t kk = KEY_WORST;
-            if (e < p.list_len) {
-                const int32_t id = p.cand_id[lbase + e];
-                if (id >= 0) kk = ((uint64_t)(~f32_ord(p.cand_score[lbase + e])) << 32) | (uint32_t)id;
-            }
-            keys[R + r] = kk;
-        }
-        if (s == 0) {
+    {
+        const int lists_per_chunk = max(1, NC / p.list_len);
+        const size_t qbase = (size_t)q * p.n_splits;
+        bool first = true;
+        for (int s0 = 0; s0 < p.n_splits; s0 += lists_per_chunk) {
+            uint64_t chunk[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                keys[r] = keys[R + r];
-                keys[R + r] = KEY_WORST;
+                const int e = r * 32 + lane;
+                const int li = e / p.list_len, pos = e - li * p.list_len;
+                uint64_t kk = KEY_WORST;
+                if (li < lists_per_chunk && s0 + li < p.n_splits) {
+                    const size_t off = (qbase + s0 + li) * p.list_len + pos;
+                    const int32_t id = p.cand_id[off];
+                    if (id >= 0) kk = ((uint64_t)(~f32_ord(p.cand_score[off])) << 32) | (uint32_t)id;
+                }
+                chunk[r] = kk;
             }
-        } else {
-            warp_bitonic_sort<2 * R>(keys, lane);
-            // best discarded candidate (element NC of the sorted 2*NC) bounds everything dropped here
-            const uint64_t first_drop = __shfl_sync(FULL, keys[R], 0);
-            if (first_drop != KEY_WORST) bound = fmaxf(bound, f32_unord(~(uint32_t)(first_drop >> 32)));
+            for (int li = lane; li < lists_per_chunk && s0 + li < p.n_splits; li += 32) bound = fmaxf(bound, p.cand_thr[qbase + s0 + li]);
+            warp_bitonic_sort<R>(chunk, lane);
+            if (first) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) keys[r] = chunk[r];
+                first = false;
+            } else {
+                // best discarded candidate bounds everything dropped by this fold
+                const uint64_t drop = warp_merge_keep_low<R>(keys, chunk, lane);
+                if (drop != KEY_WORST) bound = fmaxf(bound, f32_unord(~(uint32_t)(drop >> 32)));
+            }
         }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) bound = fmaxf(bound, __shfl_xor_sync(FULL, bound, off));
     }
-    if (p.n_splits == 1) warp_bitonic_sort<2 * R>(keys, lane);  // a single list arrives unsorted
     // margin between a filter score and the exact score it stands for (same quantity the certificate uses below)
     const double qn_m = sqrt(qn2), mx_m = (double)p.max_norm;
     const double eps_f = is_l2 ? 2.0 * (double)p.rel_eps * qn_m * mx_m + 2.4e-7 * (mx_m * mx_m + 2.0 * qn_m * mx_m) + 1e-30
