@@ -82,23 +82,46 @@ def c4(args):
     x[dst] = x[src] + noise
     x = (x / x.norm(dim=1, keepdim=True)).to(torch.bfloat16).contiguous()
     idx = nv.Index(None, nv.BF16, nv.METRIC_IP, 0, on_device_ptr=x.data_ptr(), n=n, d=d)
-    idx.threshold_pairs(0.95)  # warm-up (sizes the candidate buffer)
+    part, nparts = args.dedup_part, args.dedup_parts
+    if not args.no_warmup:
+        idx.threshold_pairs(0.95, part=part, nparts=nparts)  # warm-up
     nv.stats_reset()
     t0 = time.perf_counter()
-    pi, pj = idx.threshold_pairs(0.95)
+    pi, pj = idx.threshold_pairs(0.95, part=part, nparts=nparts)
     dt = time.perf_counter() - t0
     lab = nv.connected_components(n, pi, pj, 0)
     ncomp_dup = int((lab != np.arange(n)).sum())
-    # oracle on a slice: the relation restricted to the first 3000 rows must match exactly
+    # oracle on a slice: the relation restricted to the first 3000 rows (and to this rank's 128-row tiles) must match exactly
     sub = 3000
     xs = x[:sub].float().cpu().numpy()
     oi, oj, _ = oracle.threshold_pairs(xs, 0.95)
+    mine = (oi // 128) % nparts == part
+    oi, oj = oi[mine], oj[mine]
     keep = (pi < sub) & (pj < sub)
     ok = bool(np.array_equal(pi[keep], oi) and np.array_equal(pj[keep], oj))
-    fl = float(n) * (n - 1) / 2 * 2 * d
-    print(json.dumps({"config": "C4 sem_dedup pairs, %d x 384 bf16, tau=0.95, 1 GPU" % n, "seconds": dt, "pairs": int(len(pi)),
-                      "rows_removed": ncomp_dup, "tflops_symmetric": fl / dt / 1e12, "slice_relation_exact_vs_oracle": ok,
-                      "stats": nv.stats()}), flush=True)
+    # full-size properties: i < j, sorted unique, every pair owned by this part, every returned pair really above tau, and
+    # every planted pair above tau (recomputed with torch in fp64 from the stored bf16 rows) is present
+    tpi, tpj = torch.from_numpy(pi).to(dev), torch.from_numpy(pj).to(dev)
+    key = pi.astype(np.uint64) << np.uint64(32) | pj.astype(np.uint64)
+    shape_ok = bool((pi < pj).all() and (np.diff(key.astype(np.int64)) > 0).all() and (((pi // 128) % nparts) == part).all())
+    sc_out = torch.empty(len(pi), dtype=torch.float64, device=dev)
+    for s in range(0, len(pi), 1 << 18):
+        e = min(len(pi), s + (1 << 18))
+        sc_out[s:e] = (x[tpi[s:e]].double() * x[tpj[s:e]].double()).sum(1)
+    all_above = bool((sc_out.float() > 0.95).all()) if len(pi) else True
+    lo, hi = torch.minimum(src, dst), torch.maximum(src, dst)
+    sc_pl = torch.empty(m, dtype=torch.float64, device=dev)
+    for s in range(0, m, 1 << 18):
+        e = min(m, s + (1 << 18))
+        sc_pl[s:e] = (x[lo[s:e]].double() * x[hi[s:e]].double()).sum(1)
+    want = (sc_pl.float() > 0.95) & (lo != hi) & (((lo // 128) % nparts) == part)
+    wkey = (lo[want].cpu().numpy().astype(np.uint64) << np.uint64(32)) | hi[want].cpu().numpy().astype(np.uint64)
+    planted_found = bool(np.isin(wkey, key).all())
+    fl = float(n) * (n - 1) / 2 * 2 * d / nparts
+    print(json.dumps({"config": "C4 sem_dedup pairs, %d x 384 bf16, tau=0.95, 1 GPU, tile share %d/%d" % (n, part, nparts), "seconds": dt,
+                      "pairs": int(len(pi)), "rows_removed": ncomp_dup, "tflops_symmetric": fl / dt / 1e12,
+                      "slice_relation_exact_vs_oracle": ok, "pairs_sorted_unique_owned": shape_ok, "all_returned_above_tau_fp64": all_above,
+                      "planted_pairs_expected": int(want.sum()), "planted_pairs_all_found": planted_found, "stats": nv.stats()}), flush=True)
     idx.close()
 
 
@@ -121,12 +144,21 @@ def c5(args):
         a, c, obj = idx.kmeans(k, niter=20, full_lloyd=bool(full))
         dt = time.perf_counter() - t0
         st = nv.stats()
-        purity = float((torch.from_numpy(a).to(dev)[:200000] == torch.from_numpy(a).to(dev)[:200000]).float().mean())
+        # full-size properties: the returned assignment is a fixed point of kmeans_assign on the returned centroids
+        # (faiss: `kmeans.index.search(x, 1)`, utils.py:65) and equals the fp64 argmin on a sample
+        a2, _ = idx.kmeans_assign(c)
+        idem = bool(np.array_equal(a, a2))
+        smp = torch.arange(0, n, max(1, n // 4096), device=dev)[:4096]
+        dd = torch.cdist(x[smp].double(), torch.from_numpy(c).to(dev).double())
+        srt = dd.topk(2, dim=1, largest=False)
+        clear = ((srt.values[:, 1] - srt.values[:, 0]) > 1e-6 * srt.values[:, 1]).cpu().numpy()
+        amin_ok = bool((srt.indices[:, 0].cpu().numpy()[clear] == a[smp.cpu().numpy()][clear]).all())
         npts = n if full else min(n, 256 * k)
         fl = 2.0 * npts * k * d * 20 + 2.0 * n * k * d
         print(json.dumps({"config": "C5 k-means %d x 768 bf16, k=1024, 20 it, %s, 1 GPU" % (n, "full Lloyd" if full else "faiss parity (256k subsample)"),
                           "seconds": dt, "s_per_iteration": dt / 21, "assign_tflops_equiv": fl / dt / 1e12, "obj_first": float(obj[0]),
-                          "obj_last": float(obj[-1]), "clusters_used": int(len(np.unique(a))), "fallback_queries": st["fallback_queries"],
+                          "obj_last": float(obj[-1]), "clusters_used": int(len(np.unique(a))), "assign_is_fixed_point": idem,
+                          "assign_equals_fp64_argmin_4096_sample": amin_ok, "fallback_queries": st["fallback_queries"],
                           "launches": st["launches"]}), flush=True)
     idx.close()
 
@@ -137,6 +169,9 @@ if __name__ == "__main__":
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--n-dedup", type=int, default=1_000_000)
     ap.add_argument("--n-kmeans", type=int, default=1_000_000)
+    ap.add_argument("--dedup-part", type=int, default=0)
+    ap.add_argument("--dedup-parts", type=int, default=1, help="time one rank's share of the upper-triangular tile grid (8 = C4's 8-GPU split)")
+    ap.add_argument("--no-warmup", action="store_true")
     a = ap.parse_args()
     for w in a.which.split(","):
         {"c2": c2, "c4": c4, "c5": c5}[w](a)
