@@ -61,7 +61,8 @@ int build_view(const void* store, int64_t n, int d, int dtype, DevBuf& filt_pad,
 // relative (to ||q||*||x||) bound on |filter score - exact score| of the inner product
 float filter_rel_eps(int store_dtype, int filt_dtype, int q_dtype, int d) {
     // fp32 accumulation inside the tensor core: products are exact, every accumulation step may lose one
-    // (truncated) ulp of the running magnitude; (d + 64) * 2^-23 is generous (validated in tests/test_gpu_filter.py)
+    // (truncated) ulp of the running magnitude; (d + 64) * 2^-23 is generous. Exercised by tests/test_gpu_search.py and
+    // tests/test_gpu_fuzz.py: a too-small bound shows up as a wrong neighbour, a too-large one only as fallback work.
     const double acc = (double)(d + 64) * 1.1920929e-7;
     double ex = 0.0, eq = 0.0;  // relative representation error of the corpus / query operand seen by the MMA
     if (filt_dtype == B2_F32) {  // kind::tf32 keeps 10 explicit mantissa bits of an fp32 operand

@@ -283,9 +283,12 @@ struct FilterParams {
     int32_t n_splits;
     int32_t tiles_per_split;  // corpus tiles (of 256 rows) per split
     int32_t n_ntiles;         // ceil(n / 256)
-    // all-pairs (dedup) schedule: the query matrix IS the corpus; item i is query tile part + i*nparts and sweeps
-    // only the corpus tiles that can hold a column j > i (upper triangle)
-    int32_t pair_mode, part, nparts;
+    // all-pairs (dedup) schedule: the query matrix IS the corpus; an item is one query tile sweeping only the corpus tiles
+    // that can hold a column j > i (upper triangle). Query tiles are dealt to the `nparts` ranks in GROUPS of pair_group
+    // consecutive tiles (group g belongs to rank g % nparts): the CTAs of one rank then walk neighbouring corpus tiles at
+    // the same time and share them through L2 (dealing single tiles round-robin spreads the concurrently read corpus
+    // window nparts times wider: at 10M x 384 and 8 ranks it reached the L2 size and halved the throughput).
+    int32_t pair_mode, part, nparts, pair_group, pair_items;
     int32_t debug_mode;  // timing experiments only (B2_FILTER_DEBUG): 1 = epilogue drains TMEM but ignores the scores,
                          // 2 = accumulate per-role wait cycles into dbg[]
     unsigned long long* dbg;  // [16] cycle counters (debug_mode 2)
@@ -322,14 +325,15 @@ __device__ __forceinline__ Sched make_sched() {
     return sc;
 }
 __device__ __forceinline__ int num_items(const FilterParams& p) {
-    if (p.pair_mode) return p.n_mtiles > p.part ? (p.n_mtiles - p.part + p.nparts - 1) / p.nparts : 0;
+    if (p.pair_mode) return p.pair_items;
     return p.n_munits * p.n_splits;
 }
 template <bool TWO>
 __device__ __forceinline__ void item_range(const FilterParams& p, const Sched& sc, int item, int& m_tile, int& split, int& t0,
                                            int& t1) {
     if (p.pair_mode) {
-        m_tile = p.part + item * p.nparts;
+        const int grp = item / p.pair_group;
+        m_tile = (grp * p.nparts + p.part) * p.pair_group + (item - grp * p.pair_group);
         split = 0;
         t0 = (m_tile * BLOCK_M) / BLOCK_N;  // first corpus tile that can contain a column > row
         t1 = p.n_ntiles;
@@ -1080,6 +1084,14 @@ int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int
     return rc;
 }
 
+// query tiles per dealing group of the all-pairs schedule: one per SM, so that one wave of CTAs is one group
+// (B2_PAIR_GROUP overrides it; the tests use a small value to exercise the dealing on small matrices)
+static int pair_group_size(int device) {
+    const char* e = getenv("B2_PAIR_GROUP");
+    if (e && atoi(e) > 0) return atoi(e);
+    return sm_count(device);
+}
+
 // All pairs i < j of X whose filter inner product exceeds thr (sem_dedup). Candidates land in pair_i/pair_j (device,
 // capacity cap) in arbitrary order; *pair_count receives the total found.
 int launch_pair_filter(const MatView& X, float thr, int part, int nparts, int32_t* pair_i, int32_t* pair_j,
@@ -1109,12 +1121,18 @@ int launch_pair_filter(const MatView& X, float thr, int part, int nparts, int32_
     p.dbg = nullptr;
     p.part = part;
     p.nparts = nparts;
+    p.pair_group = pair_group_size(device);
     p.pair_thr = thr;
     p.pair_i = pair_i;
     p.pair_j = pair_j;
     p.pair_count = pair_count;
     p.pair_cap = cap;
-    const int64_t items = p.n_mtiles > part ? ceil_div(p.n_mtiles - part, nparts) : 0;
+    // this rank's query tiles: the full groups g = part (mod nparts) plus the trailing partial group if it is ours (it is
+    // then this rank's last group, so item -> tile stays a closed form)
+    const int64_t full_groups = p.n_mtiles / p.pair_group, rem = p.n_mtiles % p.pair_group;
+    const int64_t my_full = full_groups > part ? ceil_div(full_groups - part, (int64_t)nparts) : 0;
+    const int64_t items = my_full * p.pair_group + ((rem && full_groups % nparts == part) ? rem : 0);
+    p.pair_items = (int32_t)items;
     if (items <= 0) return B2_OK;
     const int grid = (int)std::min<int64_t>(items, sm_count(device));
     if (tf32) {

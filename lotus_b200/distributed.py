@@ -132,7 +132,7 @@ def merge_host_lists(scores: np.ndarray, idx: np.ndarray, metric: int):
 # ---- multi-GPU dedup and k-means ----------------------------------------------------------------------
 def sharded_threshold_pairs(index: "nv.Index", threshold: float, group=None):
     """All pairs i<j with score > threshold when EVERY rank holds the full corpus in `index` (it fits: 7.7 GB for
-    10M x 384 bf16): the upper-triangular tile grid is dealt round-robin to the ranks (`part`/`nparts` of
+    10M x 384 bf16): the upper-triangular tile grid is dealt to the ranks in groups of 148 query tiles (`part`/`nparts` of
     b2_threshold_pairs), each rank filters + verifies its tiles, then one all-gather of the sparse pair lists.
     Returns the same (pi, pj) — sorted by (i, j) — on every rank."""
     import torch

@@ -95,7 +95,7 @@ def c4(args):
     sub = 3000
     xs = x[:sub].float().cpu().numpy()
     oi, oj, _ = oracle.threshold_pairs(xs, 0.95)
-    mine = (oi // 128) % nparts == part
+    mine = nv.pair_owner(oi, nparts) == part
     oi, oj = oi[mine], oj[mine]
     keep = (pi < sub) & (pj < sub)
     ok = bool(np.array_equal(pi[keep], oi) and np.array_equal(pj[keep], oj))
@@ -103,7 +103,7 @@ def c4(args):
     # every planted pair above tau (recomputed with torch in fp64 from the stored bf16 rows) is present
     tpi, tpj = torch.from_numpy(pi).to(dev), torch.from_numpy(pj).to(dev)
     key = pi.astype(np.uint64) << np.uint64(32) | pj.astype(np.uint64)
-    shape_ok = bool((pi < pj).all() and (np.diff(key.astype(np.int64)) > 0).all() and (((pi // 128) % nparts) == part).all())
+    shape_ok = bool((pi < pj).all() and (np.diff(key.astype(np.int64)) > 0).all() and (nv.pair_owner(pi, nparts) == part).all())
     sc_out = torch.empty(len(pi), dtype=torch.float64, device=dev)
     for s in range(0, len(pi), 1 << 18):
         e = min(len(pi), s + (1 << 18))
@@ -114,7 +114,7 @@ def c4(args):
     for s in range(0, m, 1 << 18):
         e = min(m, s + (1 << 18))
         sc_pl[s:e] = (x[lo[s:e]].double() * x[hi[s:e]].double()).sum(1)
-    want = (sc_pl.float() > 0.95) & (lo != hi) & (((lo // 128) % nparts) == part)
+    want = (sc_pl.float() > 0.95) & (lo != hi) & (torch.from_numpy(nv.pair_owner(lo.cpu().numpy(), nparts)).to(dev) == part)
     wkey = (lo[want].cpu().numpy().astype(np.uint64) << np.uint64(32)) | hi[want].cpu().numpy().astype(np.uint64)
     planted_found = bool(np.isin(wkey, key).all())
     fl = float(n) * (n - 1) / 2 * 2 * d / nparts

@@ -1,5 +1,7 @@
 """The pandas operators end to end on the B200 (B200VS through the C-ABI) against oracle-derived expectations, plus
 the dedup / k-means / merge entry points."""
+import os
+
 import numpy as np
 import pandas as pd
 import pytest
@@ -92,9 +94,22 @@ def test_threshold_pairs_equal_the_exact_relation(gpu, dtype):
     oi, oj, cnt = oracle.threshold_pairs(xf, 0.9)
     assert cnt > 20 and np.array_equal(pi, oi) and np.array_equal(pj, oj)
     # sharded over 3 "ranks": the union of the parts is the same relation
-    parts = [idx.threshold_pairs(0.9, part=p, nparts=3) for p in range(3)]
-    allp = sorted(zip(np.concatenate([p[0] for p in parts]).tolist(), np.concatenate([p[1] for p in parts]).tolist()))
-    assert allp == list(zip(oi.tolist(), oj.tolist()))
+    # (query tiles are dealt in groups; B2_PAIR_GROUP=4 makes the 24 tiles of this matrix span 6 groups, default: 1 group)
+    for group in ("4", "5", None):
+        if group is None:
+            os.environ.pop("B2_PAIR_GROUP", None)
+        else:
+            os.environ["B2_PAIR_GROUP"] = group
+        try:
+            parts = [idx.threshold_pairs(0.9, part=p, nparts=3) for p in range(3)]
+            for p, (a, _) in enumerate(parts):
+                assert (gpu.pair_owner(a, 3) == p).all()
+            if group is not None:
+                assert all(len(a) for a, _ in parts)
+        finally:
+            os.environ.pop("B2_PAIR_GROUP", None)
+        allp = sorted(zip(np.concatenate([p[0] for p in parts]).tolist(), np.concatenate([p[1] for p in parts]).tolist()))
+        assert allp == list(zip(oi.tolist(), oj.tolist()))
     lab = gpu.connected_components(len(x), pi, pj)
     assert np.array_equal(lab, oracle.connected_components(len(x), oi, oj))
     idx.close()
