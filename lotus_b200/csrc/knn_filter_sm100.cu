@@ -289,6 +289,8 @@ struct FilterParams {
     // the same time and share them through L2 (dealing single tiles round-robin spreads the concurrently read corpus
     // window nparts times wider: at 10M x 384 and 8 ranks it reached the L2 size and halved the throughput).
     int32_t pair_mode, part, nparts, pair_group, pair_items;
+    int32_t pair_align;  // 1: every tile of a group starts its sweep at the group's first corpus tile (equal sweep lengths
+                         // keep the CTAs of a wave on the same corpus tile for the whole launch; costs <= group/2 extra tiles)
     int32_t debug_mode;  // timing experiments only (B2_FILTER_DEBUG): 1 = epilogue drains TMEM but ignores the scores,
                          // 2 = accumulate per-role wait cycles into dbg[]
     unsigned long long* dbg;  // [16] cycle counters (debug_mode 2)
@@ -333,9 +335,10 @@ __device__ __forceinline__ void item_range(const FilterParams& p, const Sched& s
                                            int& t1) {
     if (p.pair_mode) {
         const int grp = item / p.pair_group;
-        m_tile = (grp * p.nparts + p.part) * p.pair_group + (item - grp * p.pair_group);
+        const int first = (grp * p.nparts + p.part) * p.pair_group;
+        m_tile = first + (item - grp * p.pair_group);
         split = 0;
-        t0 = (m_tile * BLOCK_M) / BLOCK_N;  // first corpus tile that can contain a column > row
+        t0 = ((p.pair_align ? first : m_tile) * BLOCK_M) / BLOCK_N;  // first corpus tile that can contain a column > row
         t1 = p.n_ntiles;
     } else {
         const int unit = item % p.n_munits;
@@ -1122,6 +1125,10 @@ int launch_pair_filter(const MatView& X, float thr, int part, int nparts, int32_
     p.part = part;
     p.nparts = nparts;
     p.pair_group = pair_group_size(device);
+    {
+        const char* e = getenv("B2_PAIR_ALIGN");
+        p.pair_align = e ? (atoi(e) != 0) : 1;  // measured (scripts/pair_sched_exp.py): +15 % at 1M rows, neutral at 10M x 8 ranks
+    }
     p.pair_thr = thr;
     p.pair_i = pair_i;
     p.pair_j = pair_j;

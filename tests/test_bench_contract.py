@@ -28,3 +28,13 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
                        text=True, timeout=120, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_reference_arm_sizes_its_own_sample():
+    # --cpu-sample 0 (the default): the step is calibrated to ~10 s of the host cores, clamped to [128, 8192] and to nq
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--n", "20000", "--nq", "300",
+                        "--steps", "1", "--warmup", "3"], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, RANK="0", WORLD_SIZE="1"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert 128 <= d["config"]["sample_queries_per_step"] <= 300 and d["value"] > 0
