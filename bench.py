@@ -141,10 +141,12 @@ def load_peaks() -> tuple[float, str]:
 
 def pick_cpu_sample(oracle, x, q_pool, k, requested: int, target_s: float) -> int:
     """Size of the bounded CPU sample: `requested` if given, else as many queries as the host cores score in about
-    `target_s` seconds (calibrated on 64 queries against the full index), clamped to [128, 8192]."""
+    `target_s` seconds (calibrated on one query block per thread against the full index), clamped to [128, 8192]."""
     if requested > 0:
         return min(requested, len(q_pool))
-    probe = min(64, len(q_pool))
+    # one 16-query block per host thread (orc_knn_blocked parallelises over query blocks): a smaller probe would leave
+    # cores idle and underestimate the rate
+    probe = min(max(64, 16 * oracle.num_threads()), len(q_pool))
     oracle.knn_blocked(x[:50_000], q_pool[:probe], k, oracle.IP)  # spin the thread pool up
     t0 = time.perf_counter()
     oracle.knn_blocked(x, q_pool[:probe], k, oracle.IP)

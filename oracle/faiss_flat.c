@@ -304,6 +304,27 @@ static inline void dot4_fma(const float* q0, const float* q1, const float* q2, c
     out[0] = a0; out[1] = a1; out[2] = a2; out[3] = a3;
 }
 
+/* 4 queries x 2 database rows: 8 independent accumulators, 6 loads per 8 FMAs */
+static inline void dot4x2_fma(const float* q0, const float* q1, const float* q2, const float* q3, const float* xa, const float* xb,
+                              int d, float* outa, float* outb) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+#pragma omp simd reduction(+ : a0, a1, a2, a3, b0, b1, b2, b3)
+    for (int i = 0; i < d; ++i) {
+        const float xv = xa[i], yv = xb[i];
+        const float u0 = q0[i], u1 = q1[i], u2 = q2[i], u3 = q3[i];
+        a0 = __builtin_fmaf(u0, xv, a0);
+        a1 = __builtin_fmaf(u1, xv, a1);
+        a2 = __builtin_fmaf(u2, xv, a2);
+        a3 = __builtin_fmaf(u3, xv, a3);
+        b0 = __builtin_fmaf(u0, yv, b0);
+        b1 = __builtin_fmaf(u1, yv, b1);
+        b2 = __builtin_fmaf(u2, yv, b2);
+        b3 = __builtin_fmaf(u3, yv, b3);
+    }
+    outa[0] = a0; outa[1] = a1; outa[2] = a2; outa[3] = a3;
+    outb[0] = b0; outb[1] = b1; outb[2] = b2; outb[3] = b3;
+}
+
 int orc_knn_blocked(const float* x, int64_t n, int d, const float* q, int64_t nq, int k, int metric, float* D,
                     int64_t* I) {
     if (k <= 0 || d <= 0) return -1;
@@ -319,7 +340,7 @@ int orc_knn_blocked(const float* x, int64_t n, int d, const float* q, int64_t nq
     for (int64_t b = 0; b < nblocks; ++b) {
         const int64_t q0 = b * ORC_QB;
         const int qb = (int)((nq - q0) < ORC_QB ? (nq - q0) : ORC_QB);
-        float qn[ORC_QB], thresh[ORC_QB], sc[ORC_QB];
+        float qn[ORC_QB], thresh[ORC_QB], sc2[2][ORC_QB];
         const float* qp[ORC_QB];
         for (int t = 0; t < ORC_QB; ++t) qp[t] = q + (q0 + (t < qb ? t : qb - 1)) * d; /* pad the block with its last query */
         for (int t = 0; t < qb; ++t) {
@@ -327,9 +348,17 @@ int orc_knn_blocked(const float* x, int64_t n, int d, const float* q, int64_t nq
             heap_heapify(is_max, k, D + (q0 + t) * k, I + (q0 + t) * k);
             thresh[t] = D[(q0 + t) * k];
         }
-        for (int64_t j = 0; j < n; ++j) {
-            const float* xj = x + j * d;
-            for (int t = 0; t < ORC_QB; t += 4) dot4_fma(qp[t], qp[t + 1], qp[t + 2], qp[t + 3], xj, d, sc + t);
+        for (int64_t j2 = 0; j2 < n; j2 += 2) {
+            const int nr = (n - j2) < 2 ? 1 : 2; /* rows are scored two at a time, offered to the heaps in ascending id */
+            const float* xj = x + j2 * d;
+            if (nr == 2)
+                for (int t = 0; t < ORC_QB; t += 4)
+                    dot4x2_fma(qp[t], qp[t + 1], qp[t + 2], qp[t + 3], xj, xj + d, d, sc2[0] + t, sc2[1] + t);
+            else
+                for (int t = 0; t < ORC_QB; t += 4) dot4_fma(qp[t], qp[t + 1], qp[t + 2], qp[t + 3], xj, d, sc2[0] + t);
+            for (int r = 0; r < nr; ++r) {
+            const int64_t j = j2 + r;
+            const float* sc = sc2[r];
             for (int t = 0; t < qb; ++t) {
                 float s = sc[t];
                 if (metric == ORC_L2) {
@@ -347,6 +376,7 @@ int orc_knn_blocked(const float* x, int64_t n, int d, const float* q, int64_t nq
                     heap_replace_top(is_max, k, hv, hi, s, j);
                     thresh[t] = hv[0];
                 }
+            }
             }
         }
         if (k > 1)
