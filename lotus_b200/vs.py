@@ -96,6 +96,8 @@ class B200VS(VS):
     over those values), or "auto" (bf16 only when handed a bf16 tensor).
     """
 
+    accepts_id_arrays = True  # `ids=` may be a numpy int64 array (the operators then skip building a Python list)
+
     def __init__(self, factory_string: str = "Flat", metric: int = METRIC_INNER_PRODUCT, dtype: str = "auto",
                  device: int = 0, cache_size: int = 4):
         super().__init__()

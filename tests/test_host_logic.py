@@ -203,3 +203,69 @@ def test_operator_cache_passthrough_and_reference_failure_mode(env):
     with lotus.settings.context(enable_cache=True):  # lotus/cache.py:38-41: dereferences settings.lm.cache
         with pytest.raises(AttributeError):
             df.sem_index("t", str(tmp / "c"))
+
+
+# ---- sem_sim_join frame assembly: positional-take fast path == the reference's two pandas joins ------------------------
+def _random_frame(n, kind, cols, seed):
+    r = np.random.default_rng(seed)
+    data = {}
+    for c in cols:
+        t = int(r.integers(0, 5))
+        if t == 0:
+            data[c] = [f"s{r.integers(0, 100)}" for _ in range(n)]
+        elif t == 1:
+            data[c] = r.integers(0, 100, n)
+        elif t == 2:
+            data[c] = r.random(n)
+        elif t == 3:
+            data[c] = r.random(n) > 0.5
+        else:
+            data[c] = pd.Categorical(r.choice(["x", "y", "z"], n))
+    df = pd.DataFrame(data)
+    if kind == "perm":
+        df.index = r.permutation(n) * 3 + 1
+    elif kind == "str":
+        df.index = [f"k{i}" for i in r.permutation(n)]
+    elif kind == "named":
+        df.index = pd.Index(r.permutation(n), name="rid")
+    elif kind == "float":
+        df.index = r.permutation(n).astype(np.float64)
+    elif kind == "dup":
+        df.index = r.integers(0, max(1, n // 2), n)
+    return df
+
+
+def test_sim_join_take_assembly_equals_the_reference_joins():
+    from lotus_b200.sem_ops.sem_sim_join import assemble_join, assemble_take
+    rng = np.random.default_rng(7)
+    fast = 0
+    for trial in range(400):
+        nl, nr, K = int(rng.integers(1, 30)), int(rng.integers(1, 30)), int(rng.integers(1, 6))
+        lk = rng.choice(["range", "perm", "str", "named", "float", "dup"])
+        rk = rng.choice(["range", "perm", "named", "float"])
+        lc = list(rng.choice(["a", "b", "c", "d"], int(rng.integers(1, 4)), replace=False))
+        rc = list(rng.choice(["a", "e", "f", "g"], int(rng.integers(1, 4)), replace=False))
+        L, R = _random_frame(nl, lk, lc, trial * 2), _random_frame(nr, rk, rc, trial * 2 + 1)
+        if trial % 3 == 0:
+            L.attrs["index_dirs"] = {"a": "x"}
+        if trial % 5 == 0:
+            L[lc[0]] = pd.array(rng.integers(0, 9, nl), dtype="Int64")
+            L.iloc[0, L.columns.get_loc(lc[0])] = pd.NA
+        if trial % 7 == 0:
+            R[rc[0]] = pd.to_datetime("2020-01-01") + pd.to_timedelta(rng.integers(0, 99, nr), unit="D")
+        ls, rs = [("", ""), ("_l", "_r"), ("", "_r"), ("_l", "")][int(rng.integers(0, 4))]
+        keep_index, score_col = bool(rng.integers(0, 2)), "_scores" + ["", "_x"][int(rng.integers(0, 2))]
+        m = int(rng.integers(0, nl * K + 1))
+        left_pos = np.sort(rng.integers(0, nl, m)).astype(np.int64)
+        right_labels = np.asarray(R.index)[rng.integers(0, nr, m)]
+        scores = rng.random(m).astype(np.float32)
+        got = assemble_take(L, R, left_pos, right_labels, scores, score_col, ls, rs, keep_index)
+        if got is None:
+            continue
+        fast += 1
+        temp = pd.DataFrame({"_left_id": np.asarray(L.index)[left_pos] if m else np.asarray([], dtype=object),
+                             "_right_id": right_labels, score_col: scores})
+        want = assemble_join(L, R, temp, ls, rs, keep_index)
+        pd.testing.assert_frame_equal(got, want, check_exact=True, check_index_type=True, check_column_type=True)
+        assert list(got.columns) == list(want.columns) and got.attrs == want.attrs
+    assert fast > 200  # the plain case is the common one; duplicates / clashes fall back to the joins
