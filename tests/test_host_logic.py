@@ -269,3 +269,25 @@ def test_sim_join_take_assembly_equals_the_reference_joins():
         pd.testing.assert_frame_equal(got, want, check_exact=True, check_index_type=True, check_column_type=True)
         assert list(got.columns) == list(want.columns) and got.attrs == want.attrs
     assert fast > 200  # the plain case is the common one; duplicates / clashes fall back to the joins
+
+
+def test_sim_join_hands_label_arrays_to_stores_that_take_them(env):
+    rm, vs, tmp = env
+    seen = []
+
+    class ArrayVS(NumpyVS):
+        accepts_id_arrays = True  # what B200VS declares
+
+        def __call__(self, query_vectors, K, ids=None, **kw):
+            seen.append(type(ids))
+            return super().__call__(query_vectors, K, ids=ids, **kw)
+
+    left = pd.DataFrame({"a": [f"l{i}" for i in range(5)]})
+    right = pd.DataFrame({"b": [f"r{i}" for i in range(9)]}).sem_index("b", str(tmp / "r"))
+    want = left.sem_sim_join(right[right.index % 2 == 1], "a", "b", K=3)
+    avs = ArrayVS()
+    avs.dirs, avs.x, avs.index_dir = vs.dirs, vs.x, vs.index_dir
+    lotus.settings.configure(vs=avs)
+    got = left.sem_sim_join(right[right.index % 2 == 1], "a", "b", K=3)
+    assert seen == [np.ndarray]
+    pd.testing.assert_frame_equal(got, want)
