@@ -163,6 +163,7 @@ def run_reference(args) -> None:
         return
     import oracle
     oracle.build()
+    oracle.use_all_cores()  # torchrun exports OMP_NUM_THREADS=1; the reference arm is entitled to every host core
     n, d, k = args.n, args.d, args.k
     t0 = time.time()
     x = to_bf16_values(gen_rows_numpy(0, n, d, 0))
@@ -329,6 +330,7 @@ def main() -> None:
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
         oracle.build()
+        oracle.use_all_cores()
         xs = corpus.float().cpu().numpy()
         q_pool = queries[:min(8192, nq)].float().cpu().numpy()
         sample = pick_cpu_sample(oracle, xs, q_pool, k, args.cpu_sample, 15.0)

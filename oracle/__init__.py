@@ -54,6 +54,8 @@ def lib():
         i32p = ctypes.POINTER(ctypes.c_int32)
         u32p = ctypes.POINTER(ctypes.c_uint32)
         L.orc_num_threads.restype = ctypes.c_int
+        L.orc_set_num_threads.argtypes = [ctypes.c_int]
+        L.orc_set_num_threads.restype = None
         L.orc_dot_canonical.restype = ctypes.c_float
         L.orc_dot_canonical.argtypes = [f32p, f32p, ctypes.c_int]
         L.orc_l2_canonical.restype = ctypes.c_float
@@ -97,6 +99,17 @@ def _p(a: np.ndarray, ct):
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def use_all_cores() -> int:
+    """Give OpenMP every core this process may run on, whatever OMP_NUM_THREADS said (torchrun sets it to 1)."""
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        n = os.cpu_count() or 1
+    lib().orc_set_num_threads(n)
+    return num_threads()
 
 
 def to_bf16_f32(a) -> np.ndarray:

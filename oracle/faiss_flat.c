@@ -57,6 +57,15 @@
 #define ORC_SCORER_F32_SEQ 1
 #define ORC_SCORER_F32_FAST 2
 
+/* use `n` OpenMP threads from now on (torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm wants every core) */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

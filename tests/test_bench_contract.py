@@ -38,3 +38,13 @@ def test_reference_arm_sizes_its_own_sample():
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert 128 <= d["config"]["sample_queries_per_step"] <= 300 and d["value"] > 0
+
+
+def test_reference_arm_uses_every_core_even_under_torchrun_env():
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; rank 0 of the reference arm must still use the host's cores
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--n", "20000", "--nq", "300",
+                        "--cpu-sample", "64", "--steps", "1", "--warmup", "3"], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, RANK="0", WORLD_SIZE="2", OMP_NUM_THREADS="1"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
