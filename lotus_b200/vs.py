@@ -66,8 +66,28 @@ def _cuda_tensor(a: Any):
     return None
 
 
+class BF16Backed(np.ndarray):
+    """float32 matrix whose values are known to be bfloat16-representable, carrying the bf16 bit patterns alongside.
+    `B200VS.get_vectors_from_index` returns it for bf16 indexes; when the operator hands it back as query vectors
+    (sem_sim_join.py:112-118 -> :130-134) `B200VS.__call__` ships the 2-byte patterns and searches with the exact-operand
+    error bound instead of the fp32-query one. Any slicing / arithmetic drops the tag (plain float32 semantics)."""
+    bf16_bits = None
+
+    def __array_finalize__(self, obj):
+        self.bf16_bits = None
+
+    @staticmethod
+    def wrap(f32: np.ndarray, bits: np.ndarray) -> "BF16Backed":
+        out = np.ascontiguousarray(f32, dtype=np.float32).view(BF16Backed)
+        out.bf16_bits = bits
+        return out
+
+
 def _to_host_matrix(a: Any, want_bf16: bool):
     """-> (array for the C-ABI, native dtype code, float32 view of the stored values)."""
+    bits = getattr(a, "bf16_bits", None)
+    if isinstance(a, BF16Backed) and bits is not None and bits.shape == a.shape and bits.dtype == np.uint16:
+        return np.ascontiguousarray(bits), nv.BF16, np.asarray(a)
     try:
         import torch
         if isinstance(a, torch.Tensor):
@@ -185,7 +205,7 @@ class B200VS(VS):
         assert self.b2_index is not None
         ids_a = np.asarray(list(ids) if not isinstance(ids, np.ndarray) else ids, dtype=np.int64)
         out = self.b2_index.gather(ids_a)
-        return nv.bf16_bits_to_f32(out) if self.b2_index.dtype == nv.BF16 else out
+        return BF16Backed.wrap(nv.bf16_bits_to_f32(out), out) if self.b2_index.dtype == nv.BF16 else out
 
     def __call__(self, query_vectors: Any, K: int, ids: list[int] | None = None, **kwargs: Any) -> RMOutput:
         """faiss_vs.py:43-77. Returns float32 distances [Q,K] and int64 indices [Q,K] (global ids; -1 = no result).

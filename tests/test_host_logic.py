@@ -291,3 +291,18 @@ def test_sim_join_hands_label_arrays_to_stores_that_take_them(env):
     got = left.sem_sim_join(right[right.index % 2 == 1], "a", "b", K=3)
     assert seen == [np.ndarray]
     pd.testing.assert_frame_equal(got, want)
+
+
+def test_bf16_backed_query_matrix_keeps_its_bit_patterns_only_while_untouched():
+    from lotus_b200 import _native as nv
+    from lotus_b200.vs import BF16Backed, _to_host_matrix
+    bits = nv.f32_to_bf16_bits(gauss(6, 16, 3))
+    m = BF16Backed.wrap(nv.bf16_bits_to_f32(bits), bits)
+    assert isinstance(m, np.ndarray) and m.dtype == np.float32
+    # handed back untouched (what sem_sim_join does via rm.convert_query_to_query_vector): 2-byte patterns, bf16 dtype code
+    out, code, f32 = _to_host_matrix(lotus.HashRM(dim=16).convert_query_to_query_vector(m), False)
+    assert code == nv.BF16 and out.dtype == np.uint16 and np.array_equal(out, bits) and np.array_equal(f32, np.asarray(m))
+    # any derived array is a plain float32 matrix again
+    for derived in (m[1:4], m * 2.0, m.copy(), np.ascontiguousarray(m[::2])):
+        out, code, _ = _to_host_matrix(derived, False)
+        assert code == nv.F32 and out.dtype == np.float32
