@@ -231,3 +231,38 @@ def test_split_clusters_restatement():
             nsplit += 1
     assert ns == nsplit == 2
     assert np.array_equal(bits(c2), bits(c)) and np.array_equal(h2, hh) and h2.sum() == 15
+
+
+# ---- independent third-party cross-checks (SURVEY.md §8c plan item 2): none of them is faiss, all of them are somebody
+# else's brute-force kNN / k-means step, so they pin the oracle's arithmetic (not its tie rule) from outside this repo ----
+@pytest.mark.parametrize("metric", [oracle.IP, oracle.L2])
+def test_knn_agrees_with_sklearn_and_torch_brute_force(metric):
+    import torch
+    from sklearn.neighbors import NearestNeighbors
+    x, q, k = gauss(3000, 48, 70), gauss(40, 48, 71), 7
+    D, I = oracle.knn(x, q, k, metric)
+    if metric == oracle.L2:
+        nn = NearestNeighbors(n_neighbors=k, algorithm="brute", metric="sqeuclidean").fit(x.astype(np.float64))
+        Ds, Is = nn.kneighbors(q.astype(np.float64))
+        Dt, It = torch.cdist(torch.from_numpy(q).double(), torch.from_numpy(x).double()).pow(2).topk(k, dim=1, largest=False)
+    else:
+        S = q.astype(np.float64) @ x.astype(np.float64).T
+        Is = np.argsort(-S, axis=1, kind="stable")[:, :k]
+        Ds = np.take_along_axis(S, Is, axis=1)
+        Dt, It = (torch.from_numpy(q).double() @ torch.from_numpy(x).double().T).topk(k, dim=1)
+    assert np.array_equal(I, Is) and np.array_equal(I, It.numpy())  # Gaussian data: no ties, one right answer
+    assert np.allclose(D, Ds, rtol=0, atol=1e-5) and np.allclose(D, Dt.numpy(), rtol=0, atol=1e-5)  # north_star's fp32 tolerance
+
+
+def test_kmeans_assignment_step_agrees_with_sklearn():
+    from sklearn.metrics import pairwise_distances_argmin_min
+    x = gauss(4000, 24, 80, normalize=False)
+    a, c, obj = oracle.kmeans(x, 16, niter=5)
+    lab, dist = pairwise_distances_argmin_min(x.astype(np.float64), c.astype(np.float64), metric="sqeuclidean")
+    assert np.array_equal(a, lab)
+    # and the first Lloyd update: init = first k of rand_perm(n, seed + 1), centroids = means of sklearn's assignment to them
+    init = x[oracle.rand_perm(len(x), 1234 + 1)[:16]]
+    lab0, _ = pairwise_distances_argmin_min(x.astype(np.float64), init.astype(np.float64), metric="sqeuclidean")
+    means = np.stack([x[lab0 == j].astype(np.float64).mean(0) for j in range(16)])
+    _, c1, _ = oracle.kmeans(x, 16, niter=1)
+    assert np.allclose(c1, means, rtol=0, atol=1e-5)
