@@ -305,6 +305,22 @@ def main() -> None:
     h2d = q_host.numel() * q_host.element_size()
     d2h = out_s_host.numel() * 4 + out_i_host.numel() * 8
 
+    # ---- informational: the plain C-ABI host call of the plugin (b2_index_search: pageable numpy in, numpy out) --------
+    e2e_plugin = None
+    if world == 1:
+        try:
+            qb = q_host.view(torch.int16).numpy().view(np.uint16)  # bf16 bit patterns, as B200VS hands them over
+            index.index.search(qb[:1024], k, nv.BF16)
+            index.index.search(qb, k, nv.BF16)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                index.index.search(qb, k, nv.BF16)  # returns when scores + ids are in host memory
+            dt = (time.perf_counter() - t0) / args.steps
+            e2e_plugin = {"value": nq / dt, "unit": "queries/s", "ms_per_step": dt * 1e3, "clock": "host wall clock",
+                          "api": "b2_index_search (host buffers in and out, the call B200VS.__call__ makes)"}
+        except Exception as exc:  # never lose the bench line over the informational leg
+            e2e_plugin = {"error": repr(exc)[:200]}
+
     # ---- roofline of the dominant kernel (the tcgen05 filter), per rank-0 launch --------------------------------------
     peak_tf, peak_src = load_peaks()
     flops_launch = 2.0 * nq * (hi - lo) * d  # algorithmic: 2*N_local*d per query
@@ -364,6 +380,7 @@ def main() -> None:
                                     ((hi - lo) * d * 2 / 1e6, nq * d * 2 / 1e6)},
             "e2e": {"value": nq / (ms_e2e * 1e-3), "unit": "queries/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e_plugin": e2e_plugin,
             "gpu_launches": int(round(launches_per_step * args.steps)),
             "gpu_launches_per_step": launches_per_step,
             "fallback_queries": int(fallback_q),
