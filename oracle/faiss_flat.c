@@ -39,7 +39,7 @@
  *       precision class); L2 uses the expanded BLAS form with clamp.
  *   ORC_SCORER_F32_FAST (2): same as 1 but the compiler may vectorise/reassociate — the timed CPU baseline.
  *
- * Build: gcc -O3 -fopenmp -fPIC -shared (see oracle/build.py). -ffp-contract=off so that fma() calls are
+ * Build: gcc -O3 -fopenmp -fPIC -shared (oracle/__init__.py build()). -ffp-contract=off so that fma() calls are
  * the only fused operations.
  */
 #include <float.h>
