@@ -10,7 +10,7 @@ With the real `lotus` package importable, call `lotus_b200.install()` instead: i
 The compute lives in libb2lotus.so (include/lotus_b200.h); there is no CPU fallback.
 """
 from . import utils
-from .rm import RM, HashRM, TableRM
+from .rm import RM, BagOfWordsRM, HashRM, TableRM
 from .settings import settings
 from .types import RMOutput
 from .vs import METRIC_INNER_PRODUCT, METRIC_L2, VS, B200VS
@@ -32,5 +32,5 @@ def install(vs: "B200VS | None" = None, **vs_kwargs):
     return store
 
 
-__all__ = ["RM", "HashRM", "TableRM", "VS", "B200VS", "RMOutput", "settings", "utils", "install",
+__all__ = ["RM", "BagOfWordsRM", "HashRM", "TableRM", "VS", "B200VS", "RMOutput", "settings", "utils", "install",
            "METRIC_INNER_PRODUCT", "METRIC_L2"]

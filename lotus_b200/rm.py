@@ -66,3 +66,31 @@ class HashRM(RM):
             v = rng.standard_normal(self.dim).astype(np.float32)
             out[i] = v / np.linalg.norm(v)
         return out
+
+
+class BagOfWordsRM(RM):
+    """Lexical stand-in for a sentence encoder (examples only): every lower-cased word owns a fixed pseudo-random direction
+    (seeded by its crc32); a text embeds as the L2-normalised sum of its words' directions, so texts sharing words are close."""
+
+    def __init__(self, dim: int = 256):
+        super().__init__()
+        self.dim = dim
+        self._words: dict[str, np.ndarray] = {}
+
+    def _word(self, w: str) -> np.ndarray:
+        v = self._words.get(w)
+        if v is None:
+            v = np.random.default_rng(zlib.crc32(w.encode("utf-8"))).standard_normal(self.dim).astype(np.float32)
+            self._words[w] = v
+        return v
+
+    def _embed(self, docs: list[str]) -> np.ndarray:
+        out = np.zeros((len(docs), self.dim), dtype=np.float32)
+        for i, d in enumerate(docs):
+            words = [w for w in "".join(c.lower() if c.isalnum() else " " for c in str(d)).split() if w]
+            for w in words:
+                out[i] += self._word(w)
+            nrm = float(np.linalg.norm(out[i]))
+            out[i] = out[i] / nrm if nrm > 0 else self._word("")
+        return out
+

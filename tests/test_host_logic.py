@@ -306,3 +306,18 @@ def test_bf16_backed_query_matrix_keeps_its_bit_patterns_only_while_untouched():
     for derived in (m[1:4], m * 2.0, m.copy(), np.ascontiguousarray(m[::2])):
         out, code, _ = _to_host_matrix(derived, False)
         assert code == nv.F32 and out.dtype == np.float32
+
+
+def test_quickstart_example_runs_against_the_test_double(monkeypatch, capsys):
+    # examples/quickstart.py needs a B200; its control flow (all five operators) is exercised here with the oracle-backed VS
+    import lotus_b200.sem_ops.sem_dedup as sd
+    monkeypatch.setattr(sd.nv, "connected_components", lambda n, pi, pj, device=0: oracle.connected_components(n, pi, pj))
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "quickstart.py")
+    src = open(path).read()
+    assert "vs=lotus.B200VS()" in src
+    try:
+        exec(compile(src.replace("vs=lotus.B200VS()", "vs=NumpyVS()"), path, "exec"), {"NumpyVS": NumpyVS, "__name__": "__main__"})
+    finally:
+        lotus.settings.configure(rm=None, vs=None)
+    out = capsys.readouterr().out
+    assert "bread baking" in out and "vec_scores_sim_score" in out and "cluster_id" in out
