@@ -11,14 +11,15 @@ from typing import Any, Callable
 
 import pandas as pd
 
-from .settings import settings
 
 
 def operator_cache(func: Callable) -> Callable:
     @wraps(func)
     def wrapper(self, *args, **kwargs):
-        model = settings.lm
-        if settings.enable_cache and model.cache is not None:
+        from .sem_ops._common import active_settings  # the real lotus.settings when lotus is importable
+        cfg = active_settings()
+        model = cfg.lm
+        if cfg.enable_cache and model.cache is not None:
 
             def serialize(value: Any) -> Any:
                 if value is None or isinstance(value, (str, int, float, bool)):

@@ -321,3 +321,74 @@ def test_quickstart_example_runs_against_the_test_double(monkeypatch, capsys):
         lotus.settings.configure(rm=None, vs=None)
     out = capsys.readouterr().out
     assert "bread baking" in out and "vec_scores_sim_score" in out and "cluster_id" in out
+
+
+def test_operator_cache_is_pass_through_unless_enabled_and_then_keys_on_frame_and_arguments(env):
+    rm, vs, tmp = env
+    df = pd.DataFrame({"t": [f"doc{i}" for i in range(6)]}).sem_index("t", str(tmp / "c"))
+    first = df.sem_search("t", "doc3", K=2)
+
+    class DictCache:
+        def __init__(self):
+            self.d, self.gets, self.inserts = {}, 0, 0
+
+        def get(self, key):
+            self.gets += 1
+            return self.d.get(key)
+
+        def insert(self, key, value):
+            self.inserts += 1
+            self.d[key] = value
+
+    class FakeLM:
+        cache = DictCache()
+
+    # enabled without an LM: the reference dereferences settings.lm.cache (lotus/cache.py:38-41) -> AttributeError
+    lotus.settings.configure(enable_cache=True, lm=None)
+    try:
+        with pytest.raises(AttributeError):
+            df.sem_search("t", "doc3", K=2)
+        lotus.settings.configure(lm=FakeLM())
+        a = df.sem_search("t", "doc3", K=2)
+        b = df.sem_search("t", "doc3", K=2)          # same frame + arguments: served from the cache
+        c = df.sem_search("t", "doc3", K=3)          # different argument: computed
+        assert FakeLM.cache.inserts == 2 and b is a and len(c) == 3
+        pd.testing.assert_frame_equal(a, first)
+    finally:
+        lotus.settings.configure(enable_cache=False, lm=None)
+
+
+def test_sem_search_k_doubling_branch_equals_the_ids_branch_and_rerank_reorders(env):
+    rm, vs, tmp = env
+    df = pd.DataFrame({"t": [f"doc{i}" for i in range(40)]}).sem_index("t", str(tmp / "s"))
+    sub = df[df.index % 5 == 0]                       # a filtered frame: the reference needs its K-doubling loop here
+    want = sub.sem_search("t", "doc7", K=3, return_scores=True)
+
+    class NoIdsVS(NumpyVS):
+        supports_ids_search = False                   # a store like the reference's Qdrant/Weaviate ones: no ids= argument
+
+        def __call__(self, query_vectors, K, ids=None, **kw):
+            assert ids is None
+            return super().__call__(query_vectors, K, **kw)
+
+    nvs = NoIdsVS()
+    nvs.dirs, nvs.x, nvs.index_dir = vs.dirs, vs.x, vs.index_dir
+    lotus.settings.configure(vs=nvs)
+    got = sub.sem_search("t", "doc7", K=3, return_scores=True)
+    pd.testing.assert_frame_equal(got, want)
+
+    class FlipReranker:                               # sem_search.py:146-154: reranker(query, docs, n) -> .indices into docs
+        def __call__(self, query, docs, n):
+            from types import SimpleNamespace
+            return SimpleNamespace(indices=list(range(len(docs)))[::-1][:n])
+
+    with pytest.raises(ValueError, match="Reranker not found"):
+        sub.sem_search("t", "doc7", K=3, n_rerank=2)
+    lotus.settings.configure(reranker=FlipReranker())
+    try:
+        rr = sub.sem_search("t", "doc7", K=3, n_rerank=2)
+        assert rr["t"].tolist() == want["t"].tolist()[::-1][:2]
+        only = sub.sem_search("t", "doc7", n_rerank=2)   # K=None: rerank the whole frame
+        assert only["t"].tolist() == sub["t"].tolist()[::-1][:2]
+    finally:
+        lotus.settings.configure(reranker=None)

@@ -1,0 +1,160 @@
+"""Host logic of the plugin class `B200VS` (lotus_b200/vs.py) on CPU: the native `Index` is replaced by a numpy/oracle-backed
+fake, so what is checked here is everything AROUND the C-ABI calls — argument validation, the faiss-compatible directory
+layout, the per-directory cache, dtype handling, error mapping (lotus/vector_store/faiss_vs.py:13-77 is the contract).
+The same class over the real library runs in tests/test_gpu_ops.py."""
+import os
+import pickle
+import time
+
+import numpy as np
+import pytest
+
+import lotus_b200 as lotus
+import oracle
+from helpers import gauss
+from lotus_b200 import _native as nv
+from lotus_b200 import faiss_io
+from lotus_b200.vs import BF16Backed, B200VS
+
+
+class FakeIndex:
+    """Stands in for nv.Index: same constructor, attributes and methods, computed by the oracle."""
+    live = 0
+
+    def __init__(self, x, dtype, metric=nv.METRIC_IP, device=0, on_device_ptr=None, n=None, d=None):
+        assert on_device_ptr is None
+        x = np.ascontiguousarray(x)
+        assert x.dtype == (np.float32 if dtype == nv.F32 else np.uint16) and x.ndim == 2
+        self.raw, self.dtype, self.metric, self.device = x, dtype, metric, device
+        self.vals = x if dtype == nv.F32 else nv.bf16_bits_to_f32(x)
+        self.n, self.d = x.shape
+        self.closed = False
+        self.calls = []
+        FakeIndex.live += 1
+
+    def close(self):
+        if not self.closed:
+            self.closed = True
+            FakeIndex.live -= 1
+
+    def search(self, q, k, q_dtype=nv.F32, ids=None):
+        assert not self.closed
+        self.calls.append((q.dtype, q_dtype, None if ids is None else len(ids)))
+        if k > 2048:
+            raise nv.NativeError(nv.ERANGE, f"k={k} is not supported")
+        qv = q if q_dtype == nv.F32 else nv.bf16_bits_to_f32(q)
+        if ids is None:
+            return oracle.knn(self.vals, qv, k, self.metric)
+        if len(ids) and (ids.min() < 0 or ids.max() >= self.n):
+            raise nv.NativeError(nv.ERANGE, f"ids contains a position outside [0, {self.n})")
+        return oracle.knn_subset(self.vals, qv, k, ids, self.metric)
+
+    def gather(self, ids):
+        return self.raw[np.asarray(ids, dtype=np.int64)]
+
+
+@pytest.fixture
+def fake_native(monkeypatch):
+    FakeIndex.live = 0
+    monkeypatch.setattr(nv, "Index", FakeIndex)
+    monkeypatch.setattr(nv, "require_device", lambda: None)
+    yield
+    assert FakeIndex.live >= 0
+
+
+def test_constructor_rejects_what_the_flat_backend_cannot_do():
+    with pytest.raises(ValueError, match="flat"):
+        B200VS(factory_string="IVF100,Flat")
+    with pytest.raises(ValueError, match="metric"):
+        B200VS(metric=7)
+    with pytest.raises(ValueError, match="dtype"):
+        B200VS(dtype="fp8")
+    vs = B200VS()
+    assert vs.index_dir is None and vs.metric == faiss_io.METRIC_INNER_PRODUCT
+    with pytest.raises(ValueError, match="Index not loaded"):   # faiss_vs.py:54-55
+        vs(np.zeros((1, 4), np.float32), 1)
+
+
+def test_index_writes_the_reference_directory_layout_and_searches(fake_native, tmp_path):
+    x, q = gauss(50, 16, 1), gauss(4, 16, 2)
+    vs = B200VS()
+    d = str(tmp_path / "idx")
+    vs.index(None, x, d)
+    assert vs.index_dir == d and sorted(os.listdir(d)) == ["index", "vecs"]        # faiss_vs.py:27-30
+    with open(f"{d}/vecs", "rb") as fp:
+        assert np.array_equal(pickle.load(fp), x)
+    xr, metric = faiss_io.read_flat_index(f"{d}/index")
+    assert metric == 0 and np.array_equal(xr, x)
+    out = vs(q, 5)
+    D, I = oracle.knn(x, q, 5, oracle.IP)
+    assert np.array_equal(out.indices, I) and np.array_equal(out.distances, D)
+    sub = [7, 3, 30, 31]
+    out = vs(q, 3, ids=sub)
+    D, I = oracle.knn_subset(x, q, 3, np.asarray(sub), oracle.IP)
+    assert np.array_equal(out.indices, I) and np.array_equal(out.distances, D)
+    assert np.array_equal(vs.get_vectors_from_index(d, [4, 2]), x[[4, 2]])           # faiss_vs.py:38-41
+    with pytest.raises(ValueError, match="dimension"):
+        vs(gauss(2, 8, 3), 1)
+    with pytest.raises(ValueError, match="outside"):                                 # B2_ERANGE -> ValueError
+        vs(q, 1, ids=[0, 99])
+    with pytest.raises(ValueError, match="not supported"):
+        vs(q, 5000)
+
+
+def test_directories_written_by_the_reference_layout_load_and_metric_is_checked(fake_native, tmp_path):
+    x = gauss(20, 8, 4)
+    d = str(tmp_path / "faiss_made")
+    os.makedirs(d)
+    faiss_io.write_flat_index(f"{d}/index", x, faiss_io.METRIC_L2)                   # what faiss.write_index produces for IndexFlatL2
+    with open(f"{d}/vecs", "wb") as fp:
+        pickle.dump(x.astype(np.float64), fp)                                        # LiteLLMRM hands float64 to FaissVS
+    with pytest.raises(ValueError, match="metric"):
+        B200VS().load_index(d)
+    vs = B200VS(metric=faiss_io.METRIC_L2)
+    vs.load_index(d)
+    out = vs(x[:3], 2)
+    D, I = oracle.knn(x, x[:3], 2, oracle.L2)
+    assert np.array_equal(out.indices, I) and np.array_equal(out.distances, D)
+    with pytest.raises(ValueError, match="not found"):
+        vs.load_index(str(tmp_path / "missing"))
+
+
+def test_per_directory_cache_reuses_evicts_and_notices_rewrites(fake_native, tmp_path):
+    vs = B200VS(cache_size=2)
+    dirs = [str(tmp_path / f"d{i}") for i in range(3)]
+    for i, d in enumerate(dirs[:2]):
+        vs.index(None, gauss(10 + i, 8, 10 + i), d)
+    a = vs.b2_index
+    vs.load_index(dirs[0])
+    b = vs.b2_index
+    vs.load_index(dirs[1])
+    assert vs.b2_index is a and b is not a and FakeIndex.live == 2                   # flipping between two dirs builds nothing
+    vs.index(None, gauss(12, 8, 12), dirs[2])                                        # third directory: the oldest entry goes
+    assert FakeIndex.live == 2 and b.closed and not a.closed
+    # the directory is rewritten behind our back (another process re-indexed it): the stale copy must not be served
+    time.sleep(0.01)
+    newx = gauss(10, 8, 99)
+    faiss_io.write_index_dir(dirs[1], newx, newx, 0)
+    os.utime(f"{dirs[1]}/index", (time.time() + 5, time.time() + 5))
+    vs.load_index(dirs[1])
+    assert vs.b2_index is not a and np.array_equal(vs.b2_index.vals, newx)
+    vs.close()
+    assert FakeIndex.live == 0 and vs.b2_index is None
+
+
+def test_bf16_store_rounds_once_and_hands_query_bits_back(fake_native, tmp_path):
+    x = gauss(30, 16, 5)
+    vs = B200VS(dtype="bf16")
+    d = str(tmp_path / "b")
+    vs.index(None, x, d)
+    xb = nv.bf16_bits_to_f32(nv.f32_to_bf16_bits(x))
+    assert vs.b2_index.dtype == nv.BF16 and np.array_equal(vs.b2_index.vals, xb)
+    assert np.array_equal(faiss_io.read_flat_index(f"{d}/index")[0], x)               # the faiss file keeps what faiss would: fp32
+    got = vs.get_vectors_from_index(d, [1, 5, 9])
+    assert isinstance(got, BF16Backed) and got.dtype == np.float32 and np.array_equal(np.asarray(got), xb[[1, 5, 9]])
+    out = vs(got, 4)                                                                 # the operator's round trip (sem_sim_join.py:112-134)
+    assert vs.b2_index.calls[-1][:2] == (np.dtype(np.uint16), nv.BF16)
+    D, I = oracle.knn(xb, xb[[1, 5, 9]], 4, oracle.IP)
+    assert np.array_equal(out.indices, I) and np.array_equal(out.distances, D)
+    vs(np.asarray(got) * 1.0, 4)                                                     # any derived matrix: plain fp32 queries
+    assert vs.b2_index.calls[-1][:2] == (np.dtype(np.float32), nv.F32)
