@@ -158,3 +158,22 @@ def test_bf16_store_rounds_once_and_hands_query_bits_back(fake_native, tmp_path)
     assert np.array_equal(out.indices, I) and np.array_equal(out.distances, D)
     vs(np.asarray(got) * 1.0, 4)                                                     # any derived matrix: plain fp32 queries
     assert vs.b2_index.calls[-1][:2] == (np.dtype(np.float32), nv.F32)
+
+
+def test_install_configures_whichever_settings_object_the_operators_read(fake_native, monkeypatch):
+    import sys
+    import types
+    try:
+        store = lotus.install(dtype="bf16")              # no `lotus` package in this image: our own settings
+        assert isinstance(store, B200VS) and lotus.settings.vs is store and store.dtype == "bf16"
+    finally:
+        lotus.settings.configure(vs=None)
+    # with the real package importable, ITS settings and ITS utils.cluster are the ones the reference operators consult
+    seen = {}
+    fake = types.ModuleType("lotus")
+    fake.settings = types.SimpleNamespace(configure=lambda **kw: seen.update(kw), rm=None, vs=None, enable_cache=False, lm=None)
+    fake.utils = types.SimpleNamespace(cluster="the faiss one")
+    monkeypatch.setitem(sys.modules, "lotus", fake)
+    mine = B200VS()
+    assert lotus.install(mine) is mine and seen == {"vs": mine} and fake.utils.cluster is lotus.utils.cluster
+    assert lotus.settings.vs is None
