@@ -8,6 +8,7 @@
 //                       kept: a stable counting sort builds per-centroid member lists in point order, then one thread
 //                       per (centroid, dimension) adds its column sequentially -> bit-identical centroids.
 #include <algorithm>
+#include <chrono>
 #include <random>
 #include <vector>
 
@@ -264,10 +265,39 @@ int update_centroids(b2_index* idx, const void* x, const int64_t* row_ids, int64
     return B2_OK;
 }
 
+// B2_KM_TIMING=1: per-phase wall clock of b2_kmeans on stderr (each phase closed by a stream synchronise, so the phases
+// no longer overlap with the host work between them: a diagnostic, not a benchmark mode)
+struct KmTimer {
+    bool on;
+    cudaStream_t st;
+    std::chrono::steady_clock::time_point t0;
+    double acc[6] = {0, 0, 0, 0, 0, 0};  // setup, assign, assign:filter, update, split/host, final
+    KmTimer(cudaStream_t s) : st(s) {
+        const char* e = getenv("B2_KM_TIMING");
+        on = e && atoi(e) != 0;
+        t0 = std::chrono::steady_clock::now();
+    }
+    void lap(int slot) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const auto t1 = std::chrono::steady_clock::now();
+        acc[slot] += std::chrono::duration<double, std::milli>(t1 - t0).count();
+        t0 = t1;
+    }
+    void report(int64_t m, int64_t nx, int k, int d, int niter) const {
+        if (!on) return;
+        fprintf(stderr,
+                "[b2 kmeans timing] m=%lld train=%lld k=%d d=%d niter=%d | setup %.2f ms | %d x assign %.2f ms (filter kernel %.2f) | "
+                "%d x update %.2f ms | obj/split host %.2f ms | final assign %.2f ms\n",
+                (long long)m, (long long)nx, k, d, niter, acc[0], niter, acc[1], acc[2], niter, acc[3], acc[4], acc[5]);
+    }
+};
+
 int kmeans_impl(b2_index* idx, const int64_t* ids_host, int64_t m, int k, int niter, int64_t seed, int full_lloyd, int64_t* out_assign,
                 float* out_centroids, float* out_obj, KmWork& w) {
     const int d = idx->d;
     cudaStream_t st = idx->stream;
+    KmTimer tm(st);
     const size_t es = esize(idx->dtype);
     // the point set: rows ids[0..m) of the index (device id list), or all rows
     const int64_t* ids_dev = nullptr;
@@ -337,12 +367,16 @@ int kmeans_impl(b2_index* idx, const int64_t* ids_host, int64_t m, int k, int ni
         B2_TRY(w.assign.ensure((size_t)nx * sizeof(int64_t)));
         B2_TRY(w.obj.ensure(64));
         std::vector<float> hassign(k), hcent;
+        tm.lap(0);
         for (int it = 0; it < niter; ++it) {
             B2_TRY(assign_points(idx, T, nx, cent, k, w, w.dis.as<float>(), w.assign.as<int64_t>(), st));
+            tm.lap(1);
+            if (tm.on && idx->last_filter_ms > 0) tm.acc[2] += idx->last_filter_ms;
             B2_CUDA(cudaMemsetAsync(w.obj.p, 0, sizeof(double), st));
             sum_f32_kernel<<<148, 256, 0, st>>>(w.dis.as<float>(), nx, w.obj.as<double>());
             B2_LAUNCH_CHECK();
             B2_TRY(update_centroids(idx, T, nullptr, nx, w.assign.as<int64_t>(), k, w, cent, st));
+            tm.lap(3);
             double obj = 0;
             B2_CUDA(cudaMemcpyAsync(&obj, w.obj.p, sizeof(double), cudaMemcpyDeviceToHost, st));
             B2_CUDA(cudaMemcpyAsync(hassign.data(), w.hassign.p, (size_t)k * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -356,8 +390,10 @@ int kmeans_impl(b2_index* idx, const int64_t* ids_host, int64_t m, int k, int ni
                 split_clusters_host(d, k, nx, hassign, hcent);
                 B2_CUDA(cudaMemcpy(cent, hcent.data(), (size_t)k * d * sizeof(float), cudaMemcpyHostToDevice));
             }
+            tm.lap(4);
         }
     }
+    tm.lap(0);
     // lotus/utils.py:65 kmeans.index.search(vec_set, 1) over ALL m points
     DevBuf fin_dis, fin_assign;
     int rc = fin_dis.ensure((size_t)std::max<int64_t>(m, 1) * sizeof(float));
@@ -371,6 +407,8 @@ int kmeans_impl(b2_index* idx, const int64_t* ids_host, int64_t m, int k, int ni
             rc = B2_ECUDA;
         }
     }
+    tm.lap(5);
+    tm.report(m, nx, k, d, niter);
     fin_dis.release();
     fin_assign.release();
     if (rc == B2_OK && out_obj)
