@@ -277,7 +277,8 @@ struct FilterParams {
     float* cand_thr;     // [nq, n_splits]
     int32_t nq;
     int32_t n;
-    int32_t num_kb;        // K-blocks per tile = ceil(d / elements per 128 B)
+    int32_t num_kb;        // K-blocks per tile = ceil(d / elements per 128 B); 3x that in hi/lo split mode
+    int32_t split_kb;      // 0, or K-blocks per segment of the bf16 hi|lo split: segment 0 = q_hi.x_hi, 1 = q_hi.x_lo, 2 = q_lo.x_hi
     int32_t n_mtiles;      // ceil(nq / 128)
     int32_t n_munits;      // schedulable query units: n_mtiles, or ceil(n_mtiles / 2) CTA pairs in cta_group::2 mode
     int32_t n_splits;
@@ -366,15 +367,21 @@ __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap_q, const C
                 mbar_wait(&r.empty_bar[stage], phase ^ 1);
                 uint8_t* sa = r.stage_base + stage * SB;
                 uint8_t* sb = sa + STAGE_A_BYTES;
+                int ka = kb, kx = kb;  // K-block (operand column block) of the query / corpus operand
+                if (p.split_kb) {
+                    const int seg = kb / p.split_kb, rem = kb - seg * p.split_kb;
+                    ka = rem + (seg == 2 ? p.split_kb : 0);  // q_hi, q_hi, q_lo
+                    kx = rem + (seg == 1 ? p.split_kb : 0);  // x_hi, x_lo, x_hi
+                }
                 if constexpr (TWO) {
                     // the leader's full barrier counts the bytes of BOTH CTAs (2 x 32 KB); only the leader arms it
                     if (sc.rank == 0) mbar_arrive_expect_tx(&r.full_bar[stage], 2 * SB);
-                    tma_load_2d_pair(sa, tmap_q, &r.full_bar[stage], kb * KB_ELEMS, m_tile * BLOCK_M);
-                    tma_load_2d_pair(sb, tmap_x, &r.full_bar[stage], kb * KB_ELEMS, t * BLOCK_N + sc.rank * (BLOCK_N / 2));
+                    tma_load_2d_pair(sa, tmap_q, &r.full_bar[stage], ka * KB_ELEMS, m_tile * BLOCK_M);
+                    tma_load_2d_pair(sb, tmap_x, &r.full_bar[stage], kx * KB_ELEMS, t * BLOCK_N + sc.rank * (BLOCK_N / 2));
                 } else {
                     mbar_arrive_expect_tx(&r.full_bar[stage], SB);
-                    tma_load_2d(sa, tmap_q, &r.full_bar[stage], kb * KB_ELEMS, m_tile * BLOCK_M);
-                    tma_load_2d(sb, tmap_x, &r.full_bar[stage], kb * KB_ELEMS, t * BLOCK_N);
+                    tma_load_2d(sa, tmap_q, &r.full_bar[stage], ka * KB_ELEMS, m_tile * BLOCK_M);
+                    tma_load_2d(sb, tmap_x, &r.full_bar[stage], kx * KB_ELEMS, t * BLOCK_N);
                 }
                 if (++stage == NSTAGES) {
                     stage = 0;
@@ -1017,9 +1024,15 @@ int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int
     const bool tf32 = X.filt_dtype == B2_F32;
     const int kb_elems = tf32 ? 32 : 64;
     CUtensorMap tq, tx;
-    B2_TRY(make_tmap(&tq, q_filt, tf32, nq, X.d, q_pitch, BLOCK_M));
+    const bool split = X.split_dp > 0;  // bf16 hi|lo operands: both matrices are [rows, 2*split_dp] bf16
+    if (split && (tf32 || q_pitch != 2 * (int64_t)X.split_dp || X.filt_pitch != 2 * (int64_t)X.split_dp || X.split_dp % kb_elems)) {
+        set_error("internal: inconsistent hi/lo split view");
+        return B2_EINVAL;
+    }
+    const int64_t op_cols = split ? 2 * (int64_t)X.split_dp : X.d;
+    B2_TRY(make_tmap(&tq, q_filt, tf32, nq, op_cols, q_pitch, BLOCK_M));
     // pair mode: each CTA of the pair loads HALF of the 256-row corpus tile
-    B2_TRY(make_tmap(&tx, X.filt, tf32, X.n, X.d, X.filt_pitch, two_cta ? BLOCK_N / 2 : BLOCK_N));
+    B2_TRY(make_tmap(&tx, X.filt, tf32, X.n, op_cols, X.filt_pitch, two_cta ? BLOCK_N / 2 : BLOCK_N));
     FilterParams p;
     p.xnorm = X.norm2;
     p.cand_score = cand_score;
@@ -1027,7 +1040,8 @@ int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int
     p.cand_thr = cand_thr;
     p.nq = (int32_t)nq;
     p.n = (int32_t)X.n;
-    p.num_kb = (int32_t)ceil_div(X.d, kb_elems);
+    p.split_kb = split ? (int32_t)(X.split_dp / kb_elems) : 0;
+    p.num_kb = split ? 3 * p.split_kb : (int32_t)ceil_div(X.d, kb_elems);
     p.n_mtiles = (int32_t)ceil_div(nq, BLOCK_M);
     p.n_munits = two_cta ? (p.n_mtiles + 1) / 2 : p.n_mtiles;
     p.n_ntiles = (int32_t)ceil_div(X.n, BLOCK_N);
