@@ -335,11 +335,15 @@ template <bool TWO>
 __device__ __forceinline__ void item_range(const FilterParams& p, const Sched& sc, int item, int& m_tile, int& split, int& t0,
                                            int& t1) {
     if (p.pair_mode) {
+        // units are query tiles (single-CTA mode) or pairs of consecutive query tiles (cta_group::2: the two CTAs of a pair
+        // take tiles 2u and 2u+1 and sweep the same corpus tiles)
         const int grp = item / p.pair_group;
         const int first = (grp * p.nparts + p.part) * p.pair_group;
-        m_tile = first + (item - grp * p.pair_group);
+        const int unit = first + (item - grp * p.pair_group);
+        m_tile = TWO ? 2 * unit + sc.rank : unit;
         split = 0;
-        t0 = ((p.pair_align ? first : m_tile) * BLOCK_M) / BLOCK_N;  // first corpus tile that can contain a column > row
+        const int lead_tile = (p.pair_align ? first : unit) * (TWO ? 2 : 1);
+        t0 = (lead_tile * BLOCK_M) / BLOCK_N;  // first corpus tile that can contain a column > row
         t1 = p.n_ntiles;
     } else {
         const int unit = item % p.n_munits;
@@ -784,21 +788,24 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 // ---- all-pairs threshold filter (sem_dedup): same mainloop, the epilogue emits (i, j) candidates -------------------
 constexpr int PAIR_STAGES = 4;
 constexpr int PAIR_SMEM = PAIR_STAGES * STAGE_BYTES + 256;
+constexpr int PAIR_STAGES_TWO = 6;  // cta_group::2: 32 KB per stage and CTA (A 16 KB + half of B)
+constexpr int PAIR_SMEM_TWO = PAIR_STAGES_TWO * stage_bytes(true) + 256;
 
-template <bool TF32>
+template <bool TF32, bool TWO>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pair_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x, const FilterParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PAIR_STAGES * STAGE_BYTES);
+    constexpr int NST = TWO ? PAIR_STAGES_TWO : PAIR_STAGES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NST * stage_bytes(TWO));
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const Ring ring = setup_ring<PAIR_STAGES, false>(smem, bars, &tmap_q, &tmap_x, PRODUCER_WARP, MMA_WARP, ALLOC_WARP);
+    const Ring ring = setup_ring<NST, TWO>(smem, bars, &tmap_q, &tmap_x, PRODUCER_WARP, MMA_WARP, ALLOC_WARP);
     const int n_items = num_items(p);
-    const Sched sc = make_sched<false>();
+    const Sched sc = make_sched<TWO>();
     if (warp == PRODUCER_WARP) {
-        if (lane == 0) producer_loop<TF32, PAIR_STAGES, false>(&tmap_q, &tmap_x, p, ring, sc);
+        if (lane == 0) producer_loop<TF32, NST, TWO>(&tmap_q, &tmap_x, p, ring, sc);
     } else if (warp == MMA_WARP) {
-        mma_loop<TF32, PAIR_STAGES, false>(p, ring, sc);
+        if (sc.rank == 0) mma_loop<TF32, NST, TWO>(p, ring, sc);  // the leader issues for the pair
     } else if (warp < 4) {
         const int quad = warp;  // epilogue warps 0-3: TMEM quarter == warp id
         const int row = quad * 32 + lane;
@@ -807,7 +814,7 @@ pair_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         const float thr = p.pair_thr;
         for (int item = sc.worker; item < n_items; item += sc.n_workers) {
             int m_tile, split, t0, t1;
-            item_range<false>(p, sc, item, m_tile, split, t0, t1);
+            item_range<TWO>(p, sc, item, m_tile, split, t0, t1);
             const int gi = m_tile * BLOCK_M + row;  // global row of this thread
             for (int t = t0; t < t1; ++t) {
                 const int col0 = t * BLOCK_N;
@@ -822,7 +829,10 @@ pair_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                     if (c == BLOCK_N / 32 - 1) {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&ring.tmem_empty[acc]);
+                        if (lane == 0) {
+                            if constexpr (TWO) mbar_arrive_leader(&ring.tmem_empty[acc]);  // 4 warps x 2 CTAs arrive on the leader
+                            else mbar_arrive(&ring.tmem_empty[acc]);
+                        }
                     }
                     float mx = v[0];
 #pragma unroll
@@ -849,7 +859,7 @@ pair_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             }
         }
     }
-    teardown_ring<false>(ring, ALLOC_WARP);
+    teardown_ring<TWO>(ring, ALLOC_WARP);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
@@ -1128,8 +1138,11 @@ int launch_pair_filter(const MatView& X, float thr, int part, int nparts, int32_
     p.nq = (int32_t)X.n;
     p.n = (int32_t)X.n;
     p.num_kb = (int32_t)ceil_div(X.d, kb_elems);
+    static const bool two = [] { const char* e = getenv("B2_PAIR_2CTA"); return e && atoi(e) != 0; }();
+    const bool two_cta = two && ceil_div(X.n, BLOCK_M) >= 2;
+    if (two_cta) B2_TRY(make_tmap(&tx, X.filt, tf32, X.n, X.d, X.filt_pitch, BLOCK_N / 2));  // each CTA stages half a corpus tile
     p.n_mtiles = (int32_t)ceil_div(X.n, BLOCK_M);
-    p.n_munits = p.n_mtiles;
+    p.n_munits = two_cta ? (p.n_mtiles + 1) / 2 : p.n_mtiles;
     p.n_ntiles = (int32_t)ceil_div(X.n, BLOCK_N);
     p.n_splits = 1;
     p.tiles_per_split = p.n_ntiles;
@@ -1138,7 +1151,7 @@ int launch_pair_filter(const MatView& X, float thr, int part, int nparts, int32_
     p.dbg = nullptr;
     p.part = part;
     p.nparts = nparts;
-    p.pair_group = pair_group_size(device);
+    p.pair_group = two_cta ? std::max(1, pair_group_size(device) / 2) : pair_group_size(device);  // one unit per worker
     {
         const char* e = getenv("B2_PAIR_ALIGN");
         p.pair_align = e ? (atoi(e) != 0) : 1;  // measured (scripts/pair_sched_exp.py): +15 % at 1M rows, neutral at 10M x 8 ranks
@@ -1150,20 +1163,45 @@ int launch_pair_filter(const MatView& X, float thr, int part, int nparts, int32_
     p.pair_cap = cap;
     // this rank's query tiles: the full groups g = part (mod nparts) plus the trailing partial group if it is ours (it is
     // then this rank's last group, so item -> tile stays a closed form)
-    const int64_t full_groups = p.n_mtiles / p.pair_group, rem = p.n_mtiles % p.pair_group;
+    const int64_t full_groups = p.n_munits / p.pair_group, rem = p.n_munits % p.pair_group;
     const int64_t my_full = full_groups > part ? ceil_div(full_groups - part, (int64_t)nparts) : 0;
     const int64_t items = my_full * p.pair_group + ((rem && full_groups % nparts == part) ? rem : 0);
     p.pair_items = (int32_t)items;
     if (items <= 0) return B2_OK;
-    const int grid = (int)std::min<int64_t>(items, sm_count(device));
-    if (tf32) {
-        static bool a1 = false;
-        if (!a1) { B2_CUDA(cudaFuncSetAttribute(pair_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM)); a1 = true; }
-        pair_filter_kernel<true><<<grid, NUM_THREADS, PAIR_SMEM, stream>>>(tq, tx, p);
+    if (two_cta) {
+        const int pairs = (int)std::min<int64_t>(items, sm_count(device) / 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * pairs));
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = PAIR_SMEM_TWO;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (tf32) {
+            static bool a3 = false;
+            if (!a3) { B2_CUDA(cudaFuncSetAttribute(pair_filter_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_TWO)); a3 = true; }
+            B2_CUDA(cudaLaunchKernelEx(&cfg, pair_filter_kernel<true, true>, tq, tx, p));
+        } else {
+            static bool a2 = false;
+            if (!a2) { B2_CUDA(cudaFuncSetAttribute(pair_filter_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_TWO)); a2 = true; }
+            B2_CUDA(cudaLaunchKernelEx(&cfg, pair_filter_kernel<false, true>, tq, tx, p));
+        }
     } else {
-        static bool a0 = false;
-        if (!a0) { B2_CUDA(cudaFuncSetAttribute(pair_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM)); a0 = true; }
-        pair_filter_kernel<false><<<grid, NUM_THREADS, PAIR_SMEM, stream>>>(tq, tx, p);
+        const int grid = (int)std::min<int64_t>(items, sm_count(device));
+        if (tf32) {
+            static bool a1 = false;
+            if (!a1) { B2_CUDA(cudaFuncSetAttribute(pair_filter_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM)); a1 = true; }
+            pair_filter_kernel<true, false><<<grid, NUM_THREADS, PAIR_SMEM, stream>>>(tq, tx, p);
+        } else {
+            static bool a0 = false;
+            if (!a0) { B2_CUDA(cudaFuncSetAttribute(pair_filter_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM)); a0 = true; }
+            pair_filter_kernel<false, false><<<grid, NUM_THREADS, PAIR_SMEM, stream>>>(tq, tx, p);
+        }
     }
     B2_LAUNCH_CHECK();
     g_stats[ST_FILTER_LAUNCHES]++;
