@@ -153,7 +153,7 @@ int search_core(b2_index* idx, const MatView& X, int metric, const void* q_dev, 
         else if (!q_in_place) B2_TRY(launch_prep_queries(qc, q_dtype, nqc, X.d, idx->q_filt.p, filt_dtype, q_pitch, st));
         B2_CUDA(cudaEventRecord(idx->ev0, st));
         B2_TRY(launch_knn_filter(X, q_filt, q_pitch, nqc, metric, kp, n_splits, two_cta, idx->cand_score.as<float>(),
-                                 idx->cand_id.as<int32_t>(), idx->cand_thr.as<float>(), idx->device, st));
+                                 idx->cand_id.as<int32_t>(), idx->cand_thr.as<float>(), idx->device, st, /*top1=*/k == 1));
         B2_CUDA(cudaEventRecord(idx->ev1, st));
         B2_TRY(launch_finalize(X, qc, q_dtype, nqc, metric, k, kp, kp / 2, 2 * n_splits, idx->cand_score.as<float>(),
                                idx->cand_id.as<int32_t>(), idx->cand_thr.as<float>(), rel_eps, id_map, id_offset, osc, oid,

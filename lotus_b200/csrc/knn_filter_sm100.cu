@@ -282,6 +282,7 @@ struct FilterParams {
     int32_t n_mtiles;      // ceil(nq / 128)
     int32_t n_munits;      // schedulable query units: n_mtiles, or ceil(n_mtiles / 2) CTA pairs in cta_group::2 mode
     int32_t n_splits;
+    int32_t top1;             // host-side switch only: k == 1 and B2_FILTER_TOP1=1 -> the TOP1 kernel variant is launched
     int32_t tiles_per_split;  // corpus tiles (of 256 rows) per split
     int32_t n_ntiles;         // ceil(n / 256)
     // all-pairs (dedup) schedule: the query matrix IS the corpus; an item is one query tile sweeping only the corpus tiles
@@ -646,7 +647,57 @@ __device__ __forceinline__ void process_chunk32(float (&v)[32], int idx0, int va
     }
 }
 
-template <int KP, bool IS_L2, bool TF32, bool TWO>
+// k == 1 specialisation (k-means assignment: a few corpus tiles per item, where the list warm-up of the general epilogue
+// costs more than the MMAs): each row keeps its best TWO candidates and the third-best score in registers — no smem lists,
+// no pending buffer, no flush. b1 >= b2 >= b3; everything not kept scores <= b3, which is the list's discard bound.
+template <bool IS_L2>
+__device__ __forceinline__ void process_chunk32_top2(float (&v)[32], int idx0, int valid, const float* xn, float& b1, float& b2,
+                                                     float& b3, int32_t& i1, int32_t& i2) {
+    if (valid <= 0) return;  // warp-uniform
+    if constexpr (IS_L2) {
+        const float4* xn4 = reinterpret_cast<const float4*>(xn);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 x4 = xn4[j];
+            v[4 * j + 0] = fmaf(2.f, v[4 * j + 0], -x4.x);
+            v[4 * j + 1] = fmaf(2.f, v[4 * j + 1], -x4.y);
+            v[4 * j + 2] = fmaf(2.f, v[4 * j + 2], -x4.z);
+            v[4 * j + 3] = fmaf(2.f, v[4 * j + 3], -x4.w);
+        }
+    }
+    if (valid < 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j >= valid) v[j] = -INFINITY;
+    }
+    unsigned mine = 0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float m = v[8 * g];
+#pragma unroll
+        for (int jj = 1; jj < 8; ++jj) m = fmaxf(m, v[8 * g + jj]);
+        mine |= (m > b3 ? 1u : 0u) << g;
+    }
+    const unsigned active = __reduce_or_sync(0xffffffffu, mine);
+    if (active == 0) return;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        if (!(active & (1u << g))) continue;  // warp-uniform
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const float s = v[8 * g + jj];
+            const int32_t id = idx0 + 8 * g + jj;
+            const bool c3 = s > b3, c2 = s > b2, c1 = s > b1;  // strict: an equal score stays behind the earlier column
+            b3 = c2 ? b2 : (c3 ? s : b3);
+            i2 = c1 ? i1 : (c2 ? id : i2);
+            b2 = c1 ? b1 : (c2 ? s : b2);
+            i1 = c1 ? id : i1;
+            b1 = c1 ? s : b1;
+        }
+    }
+}
+
+template <int KP, bool IS_L2, bool TF32, bool TWO, bool TOP1 = false>
 __global__ void __launch_bounds__(TOPK_THREADS, 1)
 knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
                   const FilterParams p) {
@@ -701,6 +752,8 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             float thr = -INFINITY;
             int minpos = -1;  // fill phase, 0 entries (see list_insert)
             int cnt = 0;      // pending candidates of this row
+            float b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;  // TOP1: best two scores + discard bound
+            int32_t i1 = -1, i2 = -1;
             for (int t = t0; t < t1; ++t, ++tile_ctr) {
                 if ((int)(tile_ctr & 1u) != e) continue;  // the other set's tile
                 const int col0 = t * BLOCK_N;
@@ -730,7 +783,9 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 for (int h = 0; h < 4; ++h) {
                     tmem_ld_wait();                            // chunk 2h is in va
                     tmem_ld32(taddr + (2 * h + 1) * 32, vb);   // chunk 2h+1 in flight while va is processed
-                    if (p.debug_mode != 1)
+                    if constexpr (TOP1)
+                        process_chunk32_top2<IS_L2>(va, col0 + (2 * h) * 32, ncols - (2 * h) * 32, xn_tile + (2 * h) * 32, b1, b2, b3, i1, i2);
+                    else if (p.debug_mode != 1)
                         process_chunk32<KPH, IS_L2>(va, col0 + (2 * h) * 32, ncols - (2 * h) * 32, xn_tile + (2 * h) * 32, my_sc, my_id,
                                                     pend_sc, pend_id, thr, minpos, cnt, p.debug_mode == 2, dbg_flush, dbg_cols);
                     tmem_ld_wait();                            // chunk 2h+1 is in vb
@@ -745,13 +800,23 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                             else mbar_arrive(my_empty);
                         }
                     }
-                    if (p.debug_mode != 1)
+                    if constexpr (TOP1)
+                        process_chunk32_top2<IS_L2>(vb, col0 + (2 * h + 1) * 32, ncols - (2 * h + 1) * 32, xn_tile + (2 * h + 1) * 32, b1, b2, b3,
+                                                    i1, i2);
+                    else if (p.debug_mode != 1)
                         process_chunk32<KPH, IS_L2>(vb, col0 + (2 * h + 1) * 32, ncols - (2 * h + 1) * 32, xn_tile + (2 * h + 1) * 32, my_sc,
                                                     my_id, pend_sc, pend_id, thr, minpos, cnt, p.debug_mode == 2, dbg_flush, dbg_cols);
                     else if (vb[0] == 12345.678f) thr = va[1] + vb[1];  // keep the loads alive in the timing experiment
                 }
             }
-            {
+            if constexpr (TOP1) {
+                // same [KPH] list layout as the general epilogue: two real entries, the rest stays (-inf, -1)
+                my_sc[0 * BLOCK_M] = b1;
+                my_id[0 * BLOCK_M] = i1;
+                my_sc[1 * BLOCK_M] = b2;
+                my_id[1 * BLOCK_M] = i2;
+                thr = b3;
+            } else {
                 const float2 fr = flush_pending<KPH>(my_sc, my_id, pend_sc, pend_id, cnt, thr, minpos);
                 thr = fr.x;
                 minpos = __float_as_int(fr.y);
@@ -905,9 +970,9 @@ int make_tmap(CUtensorMap* map, const void* base, bool tf32, int64_t rows, int64
     return B2_OK;
 }
 
-template <int KP, bool IS_L2, bool TF32, bool TWO>
+template <int KP, bool IS_L2, bool TF32, bool TWO, bool TOP1 = false>
 int launch_variant(const CUtensorMap& tq, const CUtensorMap& tx, const FilterParams& p, int grid, cudaStream_t stream) {
-    auto kern = knn_filter_kernel<KP, IS_L2, TF32, TWO>;
+    auto kern = knn_filter_kernel<KP, IS_L2, TF32, TWO, TOP1>;
     constexpr int smem = smem_bytes(KP, TWO);
     static bool attr_set = false;
     if (!attr_set) {
@@ -935,6 +1000,16 @@ int launch_variant(const CUtensorMap& tq, const CUtensorMap& tx, const FilterPar
 template <int KP, bool TWO>
 int launch_kp(bool is_l2, bool tf32, const CUtensorMap& tq, const CUtensorMap& tx, const FilterParams& p, int grid,
               cudaStream_t stream) {
+    if constexpr (KP == 16) {
+        if (p.top1) {  // k == 1: register-resident top-2 epilogue
+            if (is_l2) {
+                return tf32 ? launch_variant<KP, true, true, TWO, true>(tq, tx, p, grid, stream)
+                            : launch_variant<KP, true, false, TWO, true>(tq, tx, p, grid, stream);
+            }
+            return tf32 ? launch_variant<KP, false, true, TWO, true>(tq, tx, p, grid, stream)
+                        : launch_variant<KP, false, false, TWO, true>(tq, tx, p, grid, stream);
+        }
+    }
     if (is_l2) {
         return tf32 ? launch_variant<KP, true, true, TWO>(tq, tx, p, grid, stream)
                     : launch_variant<KP, true, false, TWO>(tq, tx, p, grid, stream);
@@ -1025,7 +1100,7 @@ int filter_choose_splits(int64_t nq, int64_t n, int num_sms, bool two_cta) {
 
 int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int64_t nq, int metric, int kp,
                       int n_splits, bool two_cta, float* cand_score, int32_t* cand_id, float* cand_thr, int device,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, bool top1) {
     if (nq <= 0 || X.n <= 0) return B2_OK;
     if (X.n > 0x7fffff00LL || nq > 0x7fffff00LL) {
         set_error("matrix too large for 32-bit row ids (n=%lld nq=%lld)", (long long)X.n, (long long)nq);
@@ -1057,6 +1132,8 @@ int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int
     p.n_ntiles = (int32_t)ceil_div(X.n, BLOCK_N);
     p.tiles_per_split = (int32_t)ceil_div(p.n_ntiles, n_splits);
     p.n_splits = n_splits;
+    static const bool top1_on = [] { const char* e = getenv("B2_FILTER_TOP1"); return e && atoi(e) != 0; }();
+    p.top1 = (top1 && top1_on && kp == 16) ? 1 : 0;
     p.pair_mode = 0;
     p.part = 0;
     p.nparts = 1;
