@@ -231,7 +231,10 @@ def pair_owner(i, nparts: int):
     """Rank that owns the pairs (i, j > i) in `threshold_pairs(part=, nparts=)`: 128-row query tiles are dealt to the ranks in
     groups of one tile per SM (148 on B200; B2_PAIR_GROUP overrides) — mirrors launch_pair_filter in knn_filter_sm100.cu."""
     group = int(os.environ.get("B2_PAIR_GROUP", "0")) or 148
-    return ((np.asarray(i, dtype=np.int64) // 128) // group) % nparts
+    tile = np.asarray(i, dtype=np.int64) // 128
+    if int(os.environ.get("B2_PAIR_2CTA", "0")):  # CTA pairs: the unit is two consecutive query tiles, one unit per pair of SMs
+        return ((tile // 2) // max(1, group // 2)) % nparts
+    return (tile // group) % nparts
 
 
 def _index_kmeans_accumulate(self, assign, k: int, ids=None):

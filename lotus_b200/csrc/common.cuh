@@ -90,6 +90,10 @@ struct MatView {
     int32_t dtype = B2_F32;       // element type of `store`
     int32_t filt_dtype = B2_F32;  // element type of `filt`: B2_BF16 -> kind::f16 MMA, B2_F32 -> kind::tf32 MMA
     int64_t filt_pitch = 0;  // elements
+    // > 0: `filt` is the bf16 hi|lo split of an fp32 matrix, [n, 2*split_dp] (split_dp = d rounded up to a K-block of 64):
+    // columns [0, split_dp) hold bf16(x), columns [split_dp, 2*split_dp) hold bf16(x - bf16(x)). The filter then runs ONE
+    // bf16 GEMM over three K segments q_hi.x_hi + q_hi.x_lo + q_lo.x_hi (1.5x a bf16 pass, operand error ~2^-16).
+    int32_t split_dp = 0;
     float max_norm = 0.f;    // max_j ||x_j|| (upper bound), for the certification margin
 };
 
@@ -100,7 +104,7 @@ struct SearchWorkspace;
 int filter_kp_for_k(int k);  // candidate-list capacity used for a given k, 0 = k too large for the filter
 int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int64_t nq, int metric, int kp,
                       int n_splits, bool two_cta, float* cand_score, int32_t* cand_id, float* cand_thr, int device,
-                      cudaStream_t stream);
+                      cudaStream_t stream, bool top1 = false);
 bool filter_use_pair(int64_t nq);
 int filter_choose_splits(int64_t nq, int64_t n, int num_sms, bool two_cta);
 int launch_pair_filter(const MatView& X, float thr, int part, int nparts, int32_t* pair_i, int32_t* pair_j,
@@ -113,6 +117,7 @@ int launch_row_norms(const void* x, int dtype, int64_t n, int d, float* norm2, f
                      cudaStream_t stream);
 int launch_convert_pad(const void* x, int dtype, int64_t n, int d, void* out, int out_dtype, int64_t out_pitch,
                        cudaStream_t stream);
+int launch_split_bf16(const void* x, int dtype, int64_t n, int d, void* out, int64_t split_dp, cudaStream_t stream);
 int launch_gather_rows(const void* x, int dtype, int d, const int64_t* ids, int64_t m, int64_t n, void* out,
                        int* err_flag, cudaStream_t stream);
 int launch_finalize(const MatView& X, const void* q, int q_dtype, int64_t nq, int metric, int k, int kp, int list_len,

@@ -212,6 +212,20 @@ __global__ void convert_pad_kernel(const void* x, int dtype, int64_t n, int d, v
     }
 }
 
+// out[r, c] = bf16(x[r,c]) and out[r, dp + c] = bf16(x[r,c] - bf16(x[r,c])) for c < d, zero padding up to dp (see MatView)
+__global__ void split_bf16_kernel(const void* x, int dtype, int64_t n, int d, __nv_bfloat16* out, int64_t dp) {
+    const int64_t total = n * dp;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / dp;
+        const int c = (int)(t - r * dp);
+        const float v = c < d ? elem_f32(x, dtype, (size_t)(r * d + c)) : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        out[r * 2 * dp + c] = hi;
+        out[r * 2 * dp + dp + c] = lo;
+    }
+}
+
 // out[i,:] = x[ids[i],:] — one warp per row, 16-byte copies when the row size allows
 __global__ void gather_rows_kernel(const char* x, size_t row_bytes, const int64_t* ids, int64_t m, int64_t n, char* out,
                                    int* err_flag) {
@@ -853,6 +867,13 @@ int launch_row_norms(const void* x, int dtype, int64_t n, int d, float* norm2, f
     B2_CUDA(cudaMemsetAsync(max_norm_dev, 0, sizeof(float), stream));
     if (n <= 0) return B2_OK;
     row_norms_kernel<<<grid_for(n * 32, 256), 256, 0, stream>>>(x, dtype, n, d, norm2, max_norm_dev);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+int launch_split_bf16(const void* x, int dtype, int64_t n, int d, void* out, int64_t split_dp, cudaStream_t stream) {
+    if (n <= 0) return B2_OK;
+    split_bf16_kernel<<<grid_for(n * split_dp, 256), 256, 0, stream>>>(x, dtype, n, d, reinterpret_cast<__nv_bfloat16*>(out), split_dp);
     B2_LAUNCH_CHECK();
     return B2_OK;
 }

@@ -277,10 +277,12 @@ struct FilterParams {
     float* cand_thr;     // [nq, n_splits]
     int32_t nq;
     int32_t n;
-    int32_t num_kb;        // K-blocks per tile = ceil(d / elements per 128 B)
+    int32_t num_kb;        // K-blocks per tile = ceil(d / elements per 128 B); 3x that in hi/lo split mode
+    int32_t split_kb;      // 0, or K-blocks per segment of the bf16 hi|lo split: segment 0 = q_hi.x_hi, 1 = q_hi.x_lo, 2 = q_lo.x_hi
     int32_t n_mtiles;      // ceil(nq / 128)
     int32_t n_munits;      // schedulable query units: n_mtiles, or ceil(n_mtiles / 2) CTA pairs in cta_group::2 mode
     int32_t n_splits;
+    int32_t top1;             // host-side switch only: k == 1 and B2_FILTER_TOP1=1 -> the TOP1 kernel variant is launched
     int32_t tiles_per_split;  // corpus tiles (of 256 rows) per split
     int32_t n_ntiles;         // ceil(n / 256)
     // all-pairs (dedup) schedule: the query matrix IS the corpus; an item is one query tile sweeping only the corpus tiles
@@ -334,11 +336,15 @@ template <bool TWO>
 __device__ __forceinline__ void item_range(const FilterParams& p, const Sched& sc, int item, int& m_tile, int& split, int& t0,
                                            int& t1) {
     if (p.pair_mode) {
+        // units are query tiles (single-CTA mode) or pairs of consecutive query tiles (cta_group::2: the two CTAs of a pair
+        // take tiles 2u and 2u+1 and sweep the same corpus tiles)
         const int grp = item / p.pair_group;
         const int first = (grp * p.nparts + p.part) * p.pair_group;
-        m_tile = first + (item - grp * p.pair_group);
+        const int unit = first + (item - grp * p.pair_group);
+        m_tile = TWO ? 2 * unit + sc.rank : unit;
         split = 0;
-        t0 = ((p.pair_align ? first : m_tile) * BLOCK_M) / BLOCK_N;  // first corpus tile that can contain a column > row
+        const int lead_tile = (p.pair_align ? first : unit) * (TWO ? 2 : 1);
+        t0 = (lead_tile * BLOCK_M) / BLOCK_N;  // first corpus tile that can contain a column > row
         t1 = p.n_ntiles;
     } else {
         const int unit = item % p.n_munits;
@@ -366,15 +372,21 @@ __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap_q, const C
                 mbar_wait(&r.empty_bar[stage], phase ^ 1);
                 uint8_t* sa = r.stage_base + stage * SB;
                 uint8_t* sb = sa + STAGE_A_BYTES;
+                int ka = kb, kx = kb;  // K-block (operand column block) of the query / corpus operand
+                if (p.split_kb) {
+                    const int seg = kb / p.split_kb, rem = kb - seg * p.split_kb;
+                    ka = rem + (seg == 2 ? p.split_kb : 0);  // q_hi, q_hi, q_lo
+                    kx = rem + (seg == 1 ? p.split_kb : 0);  // x_hi, x_lo, x_hi
+                }
                 if constexpr (TWO) {
                     // the leader's full barrier counts the bytes of BOTH CTAs (2 x 32 KB); only the leader arms it
                     if (sc.rank == 0) mbar_arrive_expect_tx(&r.full_bar[stage], 2 * SB);
-                    tma_load_2d_pair(sa, tmap_q, &r.full_bar[stage], kb * KB_ELEMS, m_tile * BLOCK_M);
-                    tma_load_2d_pair(sb, tmap_x, &r.full_bar[stage], kb * KB_ELEMS, t * BLOCK_N + sc.rank * (BLOCK_N / 2));
+                    tma_load_2d_pair(sa, tmap_q, &r.full_bar[stage], ka * KB_ELEMS, m_tile * BLOCK_M);
+                    tma_load_2d_pair(sb, tmap_x, &r.full_bar[stage], kx * KB_ELEMS, t * BLOCK_N + sc.rank * (BLOCK_N / 2));
                 } else {
                     mbar_arrive_expect_tx(&r.full_bar[stage], SB);
-                    tma_load_2d(sa, tmap_q, &r.full_bar[stage], kb * KB_ELEMS, m_tile * BLOCK_M);
-                    tma_load_2d(sb, tmap_x, &r.full_bar[stage], kb * KB_ELEMS, t * BLOCK_N);
+                    tma_load_2d(sa, tmap_q, &r.full_bar[stage], ka * KB_ELEMS, m_tile * BLOCK_M);
+                    tma_load_2d(sb, tmap_x, &r.full_bar[stage], kx * KB_ELEMS, t * BLOCK_N);
                 }
                 if (++stage == NSTAGES) {
                     stage = 0;
@@ -635,7 +647,57 @@ __device__ __forceinline__ void process_chunk32(float (&v)[32], int idx0, int va
     }
 }
 
-template <int KP, bool IS_L2, bool TF32, bool TWO>
+// k == 1 specialisation (k-means assignment: a few corpus tiles per item, where the list warm-up of the general epilogue
+// costs more than the MMAs): each row keeps its best TWO candidates and the third-best score in registers — no smem lists,
+// no pending buffer, no flush. b1 >= b2 >= b3; everything not kept scores <= b3, which is the list's discard bound.
+template <bool IS_L2>
+__device__ __forceinline__ void process_chunk32_top2(float (&v)[32], int idx0, int valid, const float* xn, float& b1, float& b2,
+                                                     float& b3, int32_t& i1, int32_t& i2) {
+    if (valid <= 0) return;  // warp-uniform
+    if constexpr (IS_L2) {
+        const float4* xn4 = reinterpret_cast<const float4*>(xn);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 x4 = xn4[j];
+            v[4 * j + 0] = fmaf(2.f, v[4 * j + 0], -x4.x);
+            v[4 * j + 1] = fmaf(2.f, v[4 * j + 1], -x4.y);
+            v[4 * j + 2] = fmaf(2.f, v[4 * j + 2], -x4.z);
+            v[4 * j + 3] = fmaf(2.f, v[4 * j + 3], -x4.w);
+        }
+    }
+    if (valid < 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j >= valid) v[j] = -INFINITY;
+    }
+    unsigned mine = 0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float m = v[8 * g];
+#pragma unroll
+        for (int jj = 1; jj < 8; ++jj) m = fmaxf(m, v[8 * g + jj]);
+        mine |= (m > b3 ? 1u : 0u) << g;
+    }
+    const unsigned active = __reduce_or_sync(0xffffffffu, mine);
+    if (active == 0) return;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        if (!(active & (1u << g))) continue;  // warp-uniform
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const float s = v[8 * g + jj];
+            const int32_t id = idx0 + 8 * g + jj;
+            const bool c3 = s > b3, c2 = s > b2, c1 = s > b1;  // strict: an equal score stays behind the earlier column
+            b3 = c2 ? b2 : (c3 ? s : b3);
+            i2 = c1 ? i1 : (c2 ? id : i2);
+            b2 = c1 ? b1 : (c2 ? s : b2);
+            i1 = c1 ? id : i1;
+            b1 = c1 ? s : b1;
+        }
+    }
+}
+
+template <int KP, bool IS_L2, bool TF32, bool TWO, bool TOP1 = false>
 __global__ void __launch_bounds__(TOPK_THREADS, 1)
 knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
                   const FilterParams p) {
@@ -690,6 +752,8 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             float thr = -INFINITY;
             int minpos = -1;  // fill phase, 0 entries (see list_insert)
             int cnt = 0;      // pending candidates of this row
+            float b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;  // TOP1: best two scores + discard bound
+            int32_t i1 = -1, i2 = -1;
             for (int t = t0; t < t1; ++t, ++tile_ctr) {
                 if ((int)(tile_ctr & 1u) != e) continue;  // the other set's tile
                 const int col0 = t * BLOCK_N;
@@ -719,7 +783,9 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 for (int h = 0; h < 4; ++h) {
                     tmem_ld_wait();                            // chunk 2h is in va
                     tmem_ld32(taddr + (2 * h + 1) * 32, vb);   // chunk 2h+1 in flight while va is processed
-                    if (p.debug_mode != 1)
+                    if constexpr (TOP1)
+                        process_chunk32_top2<IS_L2>(va, col0 + (2 * h) * 32, ncols - (2 * h) * 32, xn_tile + (2 * h) * 32, b1, b2, b3, i1, i2);
+                    else if (p.debug_mode != 1)
                         process_chunk32<KPH, IS_L2>(va, col0 + (2 * h) * 32, ncols - (2 * h) * 32, xn_tile + (2 * h) * 32, my_sc, my_id,
                                                     pend_sc, pend_id, thr, minpos, cnt, p.debug_mode == 2, dbg_flush, dbg_cols);
                     tmem_ld_wait();                            // chunk 2h+1 is in vb
@@ -734,13 +800,23 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                             else mbar_arrive(my_empty);
                         }
                     }
-                    if (p.debug_mode != 1)
+                    if constexpr (TOP1)
+                        process_chunk32_top2<IS_L2>(vb, col0 + (2 * h + 1) * 32, ncols - (2 * h + 1) * 32, xn_tile + (2 * h + 1) * 32, b1, b2, b3,
+                                                    i1, i2);
+                    else if (p.debug_mode != 1)
                         process_chunk32<KPH, IS_L2>(vb, col0 + (2 * h + 1) * 32, ncols - (2 * h + 1) * 32, xn_tile + (2 * h + 1) * 32, my_sc,
                                                     my_id, pend_sc, pend_id, thr, minpos, cnt, p.debug_mode == 2, dbg_flush, dbg_cols);
                     else if (vb[0] == 12345.678f) thr = va[1] + vb[1];  // keep the loads alive in the timing experiment
                 }
             }
-            {
+            if constexpr (TOP1) {
+                // same [KPH] list layout as the general epilogue: two real entries, the rest stays (-inf, -1)
+                my_sc[0 * BLOCK_M] = b1;
+                my_id[0 * BLOCK_M] = i1;
+                my_sc[1 * BLOCK_M] = b2;
+                my_id[1 * BLOCK_M] = i2;
+                thr = b3;
+            } else {
                 const float2 fr = flush_pending<KPH>(my_sc, my_id, pend_sc, pend_id, cnt, thr, minpos);
                 thr = fr.x;
                 minpos = __float_as_int(fr.y);
@@ -777,21 +853,24 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 // ---- all-pairs threshold filter (sem_dedup): same mainloop, the epilogue emits (i, j) candidates -------------------
 constexpr int PAIR_STAGES = 4;
 constexpr int PAIR_SMEM = PAIR_STAGES * STAGE_BYTES + 256;
+constexpr int PAIR_STAGES_TWO = 6;  // cta_group::2: 32 KB per stage and CTA (A 16 KB + half of B)
+constexpr int PAIR_SMEM_TWO = PAIR_STAGES_TWO * stage_bytes(true) + 256;
 
-template <bool TF32>
+template <bool TF32, bool TWO>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pair_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x, const FilterParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PAIR_STAGES * STAGE_BYTES);
+    constexpr int NST = TWO ? PAIR_STAGES_TWO : PAIR_STAGES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NST * stage_bytes(TWO));
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const Ring ring = setup_ring<PAIR_STAGES, false>(smem, bars, &tmap_q, &tmap_x, PRODUCER_WARP, MMA_WARP, ALLOC_WARP);
+    const Ring ring = setup_ring<NST, TWO>(smem, bars, &tmap_q, &tmap_x, PRODUCER_WARP, MMA_WARP, ALLOC_WARP);
     const int n_items = num_items(p);
-    const Sched sc = make_sched<false>();
+    const Sched sc = make_sched<TWO>();
     if (warp == PRODUCER_WARP) {
-        if (lane == 0) producer_loop<TF32, PAIR_STAGES, false>(&tmap_q, &tmap_x, p, ring, sc);
+        if (lane == 0) producer_loop<TF32, NST, TWO>(&tmap_q, &tmap_x, p, ring, sc);
     } else if (warp == MMA_WARP) {
-        mma_loop<TF32, PAIR_STAGES, false>(p, ring, sc);
+        if (sc.rank == 0) mma_loop<TF32, NST, TWO>(p, ring, sc);  // the leader issues for the pair
     } else if (warp < 4) {
         const int quad = warp;  // epilogue warps 0-3: TMEM quarter == warp id
         const int row = quad * 32 + lane;
@@ -800,7 +879,7 @@ pair_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         const float thr = p.pair_thr;
         for (int item = sc.worker; item < n_items; item += sc.n_workers) {
             int m_tile, split, t0, t1;
-            item_range<false>(p, sc, item, m_tile, split, t0, t1);
+            item_range<TWO>(p, sc, item, m_tile, split, t0, t1);
             const int gi = m_tile * BLOCK_M + row;  // global row of this thread
             for (int t = t0; t < t1; ++t) {
                 const int col0 = t * BLOCK_N;
@@ -815,7 +894,10 @@ pair_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                     if (c == BLOCK_N / 32 - 1) {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&ring.tmem_empty[acc]);
+                        if (lane == 0) {
+                            if constexpr (TWO) mbar_arrive_leader(&ring.tmem_empty[acc]);  // 4 warps x 2 CTAs arrive on the leader
+                            else mbar_arrive(&ring.tmem_empty[acc]);
+                        }
                     }
                     float mx = v[0];
 #pragma unroll
@@ -842,7 +924,7 @@ pair_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             }
         }
     }
-    teardown_ring<false>(ring, ALLOC_WARP);
+    teardown_ring<TWO>(ring, ALLOC_WARP);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
@@ -888,9 +970,9 @@ int make_tmap(CUtensorMap* map, const void* base, bool tf32, int64_t rows, int64
     return B2_OK;
 }
 
-template <int KP, bool IS_L2, bool TF32, bool TWO>
+template <int KP, bool IS_L2, bool TF32, bool TWO, bool TOP1 = false>
 int launch_variant(const CUtensorMap& tq, const CUtensorMap& tx, const FilterParams& p, int grid, cudaStream_t stream) {
-    auto kern = knn_filter_kernel<KP, IS_L2, TF32, TWO>;
+    auto kern = knn_filter_kernel<KP, IS_L2, TF32, TWO, TOP1>;
     constexpr int smem = smem_bytes(KP, TWO);
     static bool attr_set = false;
     if (!attr_set) {
@@ -918,6 +1000,16 @@ int launch_variant(const CUtensorMap& tq, const CUtensorMap& tx, const FilterPar
 template <int KP, bool TWO>
 int launch_kp(bool is_l2, bool tf32, const CUtensorMap& tq, const CUtensorMap& tx, const FilterParams& p, int grid,
               cudaStream_t stream) {
+    if constexpr (KP == 16) {
+        if (p.top1) {  // k == 1: register-resident top-2 epilogue
+            if (is_l2) {
+                return tf32 ? launch_variant<KP, true, true, TWO, true>(tq, tx, p, grid, stream)
+                            : launch_variant<KP, true, false, TWO, true>(tq, tx, p, grid, stream);
+            }
+            return tf32 ? launch_variant<KP, false, true, TWO, true>(tq, tx, p, grid, stream)
+                        : launch_variant<KP, false, false, TWO, true>(tq, tx, p, grid, stream);
+        }
+    }
     if (is_l2) {
         return tf32 ? launch_variant<KP, true, true, TWO>(tq, tx, p, grid, stream)
                     : launch_variant<KP, true, false, TWO>(tq, tx, p, grid, stream);
@@ -1008,7 +1100,7 @@ int filter_choose_splits(int64_t nq, int64_t n, int num_sms, bool two_cta) {
 
 int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int64_t nq, int metric, int kp,
                       int n_splits, bool two_cta, float* cand_score, int32_t* cand_id, float* cand_thr, int device,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, bool top1) {
     if (nq <= 0 || X.n <= 0) return B2_OK;
     if (X.n > 0x7fffff00LL || nq > 0x7fffff00LL) {
         set_error("matrix too large for 32-bit row ids (n=%lld nq=%lld)", (long long)X.n, (long long)nq);
@@ -1017,9 +1109,15 @@ int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int
     const bool tf32 = X.filt_dtype == B2_F32;
     const int kb_elems = tf32 ? 32 : 64;
     CUtensorMap tq, tx;
-    B2_TRY(make_tmap(&tq, q_filt, tf32, nq, X.d, q_pitch, BLOCK_M));
+    const bool split = X.split_dp > 0;  // bf16 hi|lo operands: both matrices are [rows, 2*split_dp] bf16
+    if (split && (tf32 || q_pitch != 2 * (int64_t)X.split_dp || X.filt_pitch != 2 * (int64_t)X.split_dp || X.split_dp % kb_elems)) {
+        set_error("internal: inconsistent hi/lo split view");
+        return B2_EINVAL;
+    }
+    const int64_t op_cols = split ? 2 * (int64_t)X.split_dp : X.d;
+    B2_TRY(make_tmap(&tq, q_filt, tf32, nq, op_cols, q_pitch, BLOCK_M));
     // pair mode: each CTA of the pair loads HALF of the 256-row corpus tile
-    B2_TRY(make_tmap(&tx, X.filt, tf32, X.n, X.d, X.filt_pitch, two_cta ? BLOCK_N / 2 : BLOCK_N));
+    B2_TRY(make_tmap(&tx, X.filt, tf32, X.n, op_cols, X.filt_pitch, two_cta ? BLOCK_N / 2 : BLOCK_N));
     FilterParams p;
     p.xnorm = X.norm2;
     p.cand_score = cand_score;
@@ -1027,12 +1125,15 @@ int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int
     p.cand_thr = cand_thr;
     p.nq = (int32_t)nq;
     p.n = (int32_t)X.n;
-    p.num_kb = (int32_t)ceil_div(X.d, kb_elems);
+    p.split_kb = split ? (int32_t)(X.split_dp / kb_elems) : 0;
+    p.num_kb = split ? 3 * p.split_kb : (int32_t)ceil_div(X.d, kb_elems);
     p.n_mtiles = (int32_t)ceil_div(nq, BLOCK_M);
     p.n_munits = two_cta ? (p.n_mtiles + 1) / 2 : p.n_mtiles;
     p.n_ntiles = (int32_t)ceil_div(X.n, BLOCK_N);
     p.tiles_per_split = (int32_t)ceil_div(p.n_ntiles, n_splits);
     p.n_splits = n_splits;
+    static const bool top1_on = [] { const char* e = getenv("B2_FILTER_TOP1"); return e && atoi(e) != 0; }();
+    p.top1 = (top1 && top1_on && kp == 16) ? 1 : 0;
     p.pair_mode = 0;
     p.part = 0;
     p.nparts = 1;
@@ -1114,8 +1215,11 @@ int launch_pair_filter(const MatView& X, float thr, int part, int nparts, int32_
     p.nq = (int32_t)X.n;
     p.n = (int32_t)X.n;
     p.num_kb = (int32_t)ceil_div(X.d, kb_elems);
+    static const bool two = [] { const char* e = getenv("B2_PAIR_2CTA"); return e && atoi(e) != 0; }();
+    const bool two_cta = two && ceil_div(X.n, BLOCK_M) >= 2;
+    if (two_cta) B2_TRY(make_tmap(&tx, X.filt, tf32, X.n, X.d, X.filt_pitch, BLOCK_N / 2));  // each CTA stages half a corpus tile
     p.n_mtiles = (int32_t)ceil_div(X.n, BLOCK_M);
-    p.n_munits = p.n_mtiles;
+    p.n_munits = two_cta ? (p.n_mtiles + 1) / 2 : p.n_mtiles;
     p.n_ntiles = (int32_t)ceil_div(X.n, BLOCK_N);
     p.n_splits = 1;
     p.tiles_per_split = p.n_ntiles;
@@ -1124,7 +1228,7 @@ int launch_pair_filter(const MatView& X, float thr, int part, int nparts, int32_
     p.dbg = nullptr;
     p.part = part;
     p.nparts = nparts;
-    p.pair_group = pair_group_size(device);
+    p.pair_group = two_cta ? std::max(1, pair_group_size(device) / 2) : pair_group_size(device);  // one unit per worker
     {
         const char* e = getenv("B2_PAIR_ALIGN");
         p.pair_align = e ? (atoi(e) != 0) : 1;  // measured (scripts/pair_sched_exp.py): +15 % at 1M rows, neutral at 10M x 8 ranks
@@ -1136,20 +1240,45 @@ int launch_pair_filter(const MatView& X, float thr, int part, int nparts, int32_
     p.pair_cap = cap;
     // this rank's query tiles: the full groups g = part (mod nparts) plus the trailing partial group if it is ours (it is
     // then this rank's last group, so item -> tile stays a closed form)
-    const int64_t full_groups = p.n_mtiles / p.pair_group, rem = p.n_mtiles % p.pair_group;
+    const int64_t full_groups = p.n_munits / p.pair_group, rem = p.n_munits % p.pair_group;
     const int64_t my_full = full_groups > part ? ceil_div(full_groups - part, (int64_t)nparts) : 0;
     const int64_t items = my_full * p.pair_group + ((rem && full_groups % nparts == part) ? rem : 0);
     p.pair_items = (int32_t)items;
     if (items <= 0) return B2_OK;
-    const int grid = (int)std::min<int64_t>(items, sm_count(device));
-    if (tf32) {
-        static bool a1 = false;
-        if (!a1) { B2_CUDA(cudaFuncSetAttribute(pair_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM)); a1 = true; }
-        pair_filter_kernel<true><<<grid, NUM_THREADS, PAIR_SMEM, stream>>>(tq, tx, p);
+    if (two_cta) {
+        const int pairs = (int)std::min<int64_t>(items, sm_count(device) / 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * pairs));
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = PAIR_SMEM_TWO;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (tf32) {
+            static bool a3 = false;
+            if (!a3) { B2_CUDA(cudaFuncSetAttribute(pair_filter_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_TWO)); a3 = true; }
+            B2_CUDA(cudaLaunchKernelEx(&cfg, pair_filter_kernel<true, true>, tq, tx, p));
+        } else {
+            static bool a2 = false;
+            if (!a2) { B2_CUDA(cudaFuncSetAttribute(pair_filter_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_TWO)); a2 = true; }
+            B2_CUDA(cudaLaunchKernelEx(&cfg, pair_filter_kernel<false, true>, tq, tx, p));
+        }
     } else {
-        static bool a0 = false;
-        if (!a0) { B2_CUDA(cudaFuncSetAttribute(pair_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM)); a0 = true; }
-        pair_filter_kernel<false><<<grid, NUM_THREADS, PAIR_SMEM, stream>>>(tq, tx, p);
+        const int grid = (int)std::min<int64_t>(items, sm_count(device));
+        if (tf32) {
+            static bool a1 = false;
+            if (!a1) { B2_CUDA(cudaFuncSetAttribute(pair_filter_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM)); a1 = true; }
+            pair_filter_kernel<true, false><<<grid, NUM_THREADS, PAIR_SMEM, stream>>>(tq, tx, p);
+        } else {
+            static bool a0 = false;
+            if (!a0) { B2_CUDA(cudaFuncSetAttribute(pair_filter_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM)); a0 = true; }
+            pair_filter_kernel<false, false><<<grid, NUM_THREADS, PAIR_SMEM, stream>>>(tq, tx, p);
+        }
     }
     B2_LAUNCH_CHECK();
     g_stats[ST_FILTER_LAUNCHES]++;
