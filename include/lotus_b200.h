@@ -148,6 +148,12 @@ B2_API int b2_kmeans_assign(b2_index* idx, const int64_t* ids, int64_t m, const 
 B2_API int b2_kmeans_accumulate(b2_index* idx, const int64_t* ids, int64_t m, const int64_t* assign, int32_t k, float* out_sums,
                          float* out_counts);
 
+/* ---- host-side marshalling (no device work) ------------------------------------------------------------ */
+/* out[i] = bfloat16 bit pattern of x[i] (round to nearest even, NaN stays a quiet NaN); *all_exact (nullable) = 1 when
+ * every x[i] was already bfloat16-representable, i.e. the 2-byte form loses nothing. The plugin uses it to ship query
+ * vectors that came out of a bf16 index (faiss_vs.py:38-41 -> sem_sim_join.py:130-134) in their exact 2-byte form. */
+B2_API int b2_host_f32_to_bf16(const float* x, int64_t count, uint16_t* out, int32_t* all_exact);
+
 /* ---- instrumentation ---------------------------------------------------------------------------------- */
 /* counters since the last b2_stats_reset(): [0] kernels launched by this library, [1] queries answered,
  * [2] queries that took the exact dense fallback, [3] tcgen05 filter launches, [4] rows rescored exactly.

@@ -5,8 +5,10 @@
     lotus.settings.configure(rm=rm, vs=lotus.B200VS())
     df.sem_index("text", "idx_dir").sem_sim_join(other, "a", "b", K=32)
 
-With the real `lotus` package importable, call `lotus_b200.install()` instead: it plugs `B200VS` into
-`lotus.settings`, replaces `lotus.utils.cluster` and re-registers the accessors that need the streaming kernels.
+With the real `lotus` package importable, call `lotus_b200.install()` instead: it imports lotus (whose import registers
+the reference's accessors), plugs `B200VS` into `lotus.settings`, replaces `lotus.utils.cluster` and THEN re-registers this
+package's accessors, so that `sem_dedup` / `sem_search` / `sem_cluster_by` reach the streaming kernels (every accessor here
+falls back to the reference's control flow when the configured store is not a B200VS).
 The compute lives in libb2lotus.so (include/lotus_b200.h); there is no CPU fallback.
 """
 from . import utils
@@ -24,11 +26,17 @@ def install(vs: "B200VS | None" = None, **vs_kwargs):
     lotus is importable, ours otherwise) and route lotus.utils.cluster to the device k-means."""
     store = vs if vs is not None else B200VS(**vs_kwargs)
     try:
-        import lotus as _ref  # type: ignore
-        _ref.settings.configure(vs=store)
-        _ref.utils.cluster = utils.cluster
+        import lotus as _ref  # type: ignore  (registers the reference's accessors: must come BEFORE register_all)
+        import lotus.utils as _ref_utils  # type: ignore
     except Exception:
+        _ref = None
+    if _ref is not None:
+        _ref.settings.configure(vs=store)
+        _ref_utils.cluster = utils.cluster  # sem_cluster_by.py:74 resolves lotus.utils.cluster at call time
+        _ref.utils = _ref_utils
+    else:
         settings.configure(vs=store)
+    sem_ops.register_all()
     return store
 
 

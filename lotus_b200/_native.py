@@ -20,7 +20,7 @@ SYMBOLS = [
     "b2_abi_version", "b2_last_error", "b2_device_count", "b2_max_k", "b2_index_create", "b2_index_free",
     "b2_index_ntotal", "b2_index_dim", "b2_index_dtype", "b2_index_metric", "b2_index_device", "b2_index_data_dev",
     "b2_index_search", "b2_index_search_dev", "b2_merge_topk_dev", "b2_index_gather", "b2_threshold_pairs",
-    "b2_connected_components", "b2_kmeans", "b2_kmeans_assign", "b2_kmeans_accumulate", "b2_stats", "b2_stats_reset", "b2_last_filter_ms",
+    "b2_connected_components", "b2_kmeans", "b2_kmeans_assign", "b2_kmeans_accumulate", "b2_stats", "b2_stats_reset", "b2_last_filter_ms", "b2_host_f32_to_bf16",
 ]
 
 
@@ -76,6 +76,8 @@ def lib() -> ctypes.CDLL:
     L.b2_kmeans_assign.argtypes = [vp, vp, i64, vp, i32, vp, vp]
     L.b2_kmeans_accumulate.restype = c.c_int
     L.b2_kmeans_accumulate.argtypes = [vp, vp, i64, vp, i32, vp, vp]
+    L.b2_host_f32_to_bf16.restype = c.c_int
+    L.b2_host_f32_to_bf16.argtypes = [vp, i64, vp, c.POINTER(i32)]
     L.b2_stats.restype = c.c_int
     L.b2_stats.argtypes = [c.POINTER(i64), i32]
     L.b2_stats_reset.restype = None
@@ -111,12 +113,19 @@ def stats_reset() -> None:
 
 
 # ---- bf16 helpers (numpy has no bfloat16: bit patterns travel as uint16) ------------------------------------------
+def f32_to_bf16_checked(a: np.ndarray) -> tuple[np.ndarray, bool]:
+    """Round-to-nearest-even float32 -> bfloat16 bit patterns (uint16; NaN stays a quiet NaN) plus whether every value
+    was already bfloat16-representable. Host marshalling done by the library's threaded helper (no device work)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    out = np.empty(a.shape, dtype=np.uint16)
+    exact = ctypes.c_int32(0)
+    check(lib().b2_host_f32_to_bf16(_ptr(a), a.size, _ptr(out), ctypes.byref(exact)))
+    return out, bool(exact.value)
+
+
 def f32_to_bf16_bits(a: np.ndarray) -> np.ndarray:
     """Round-to-nearest-even float32 -> bfloat16 bit patterns (uint16)."""
-    a = np.ascontiguousarray(a, dtype=np.float32)
-    u = a.view(np.uint32).astype(np.uint64)
-    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
-    return r.reshape(a.shape)
+    return f32_to_bf16_checked(a)[0]
 
 
 def bf16_bits_to_f32(b: np.ndarray) -> np.ndarray:

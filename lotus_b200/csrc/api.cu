@@ -4,7 +4,9 @@
 // Reference call sites replaced: lotus/vector_store/faiss_vs.py:22-77 (see the header for the mapping).
 #include <algorithm>
 #include <cstring>
+#include <atomic>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "index.cuh"
@@ -407,6 +409,43 @@ int b2_index_gather(b2_index* idx, const int64_t* ids, int64_t m, void* out, int
     if (!out_on_device) B2_CUDA(cudaMemcpyAsync(out, out_dev, (size_t)m * row_bytes, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
     if (herr) { set_error("ids contains a position outside [0, %lld)", (long long)idx->n); return B2_ERANGE; }
+    return B2_OK;
+}
+
+// Host-side marshalling helper (no device work): round-to-nearest-even fp32 -> bf16 bit patterns, NaN kept quiet, and
+// report whether every value was already bf16-representable (then the 2-byte form is EXACT and the plugin ships it).
+int b2_host_f32_to_bf16(const float* x, int64_t count, uint16_t* out, int32_t* all_exact) {
+    if (count < 0 || (count > 0 && (!x || !out))) { set_error("bad conversion arguments"); return B2_EINVAL; }
+    const int64_t kChunk = 1 << 20;
+    const int64_t nchunks = (count + kChunk - 1) / kChunk;
+    unsigned hw = std::thread::hardware_concurrency();
+    const int nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(hw ? hw : 1, 16), nchunks));
+    std::atomic<int64_t> next{0};
+    std::atomic<int> inexact{0};
+    auto work = [&]() {
+        int local_inexact = 0;
+        for (;;) {
+            const int64_t c = next.fetch_add(1);
+            if (c >= nchunks) break;
+            const int64_t lo = c * kChunk, hi = std::min(count, lo + kChunk);
+            const uint32_t* u = reinterpret_cast<const uint32_t*>(x);
+            for (int64_t i = lo; i < hi; ++i) {
+                const uint32_t v = u[i];
+                local_inexact |= (v & 0xffffu) != 0;
+                const bool is_nan = (v & 0x7fffffffu) > 0x7f800000u;
+                out[i] = is_nan ? (uint16_t)((v >> 16) | 0x0040u) : (uint16_t)((v + 0x7fffu + ((v >> 16) & 1u)) >> 16);
+            }
+        }
+        if (local_inexact) inexact.store(1);
+    };
+    if (nthreads <= 1) {
+        work();
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; ++t) pool.emplace_back(work);
+        for (auto& t : pool) t.join();
+    }
+    if (all_exact) *all_exact = inexact.load() ? 0 : 1;
     return B2_OK;
 }
 

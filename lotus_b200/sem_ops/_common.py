@@ -35,13 +35,30 @@ def resolve_rm_vs(strict: bool = False):
     return rm, vs
 
 
+_REGISTRY: dict[str, type] = {}
+
+
+def _register_now(name: str, cls: type):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return pd.api.extensions.register_dataframe_accessor(name)(cls)
+
+
 def register(name: str):
     """pd.api.extensions.register_dataframe_accessor without the override warning (the reference registers the same names)."""
     def deco(cls):
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            return pd.api.extensions.register_dataframe_accessor(name)(cls)
+        _REGISTRY[name] = cls
+        return _register_now(name, cls)
     return deco
+
+
+def register_all() -> list[str]:
+    """(Re-)register every accessor of this package. `import lotus` registers the reference's classes under the same names
+    (lotus/sem_ops/*.py), so whoever imports lotus AFTER lotus_b200 gets the reference's N^2 sem_dedup and K-doubling
+    sem_search back; `lotus_b200.install()` calls this after importing lotus."""
+    for name, cls in _REGISTRY.items():
+        _register_now(name, cls)
+    return sorted(_REGISTRY)
 
 
 def validate_df(obj: Any) -> None:

@@ -28,8 +28,6 @@ class SemDedupByDataframe:
     @operator_cache
     def __call__(self, col_name: str, threshold: float) -> pd.DataFrame:
         rm, vs = resolve_rm_vs()
-        if not hasattr(vs, "threshold_pairs"):
-            raise ValueError("sem_dedup needs a vector store with threshold_pairs (B200VS)")
         try:
             col_index_dir = self._obj.attrs["index_dirs"][col_name]
         except KeyError:
@@ -42,19 +40,39 @@ class SemDedupByDataframe:
         if n == 0:
             return self._obj
         rows = np.asarray(self._obj.index, dtype=np.int64)  # positions into the index (un-reset RangeIndex contract)
-        pi, pj = vs.threshold_pairs(float(threshold))       # pairs over INDEX positions, i < j
-        # restrict to this frame's rows and translate to frame-local row numbers
-        pos = np.full(int(max(rows.max(), pi.max() if len(pi) else 0, pj.max() if len(pj) else 0)) + 1, -1, dtype=np.int64)
-        pos[rows] = np.arange(n)
-        li, lj = pos[pi], pos[pj]
-        ok = (li >= 0) & (lj >= 0)
-        li, lj = li[ok], lj[ok]
-        # nodes are distinct text values, numbered in order of first appearance (sem_dedup.py:47,51-56)
+        if hasattr(vs, "threshold_pairs"):
+            try:
+                pi, pj = vs.threshold_pairs(float(threshold))   # pairs over INDEX positions, i < j
+            except nv.NativeError as e:
+                if e.code in (nv.EINVAL, nv.ERANGE):  # e.g. an L2 index: the relation is defined on inner products
+                    raise ValueError(e.msg) from e
+                raise
+            # restrict to this frame's rows and translate to frame-local row numbers
+            pos = np.full(int(max(rows.max(), pi.max() if len(pi) else 0, pj.max() if len(pj) else 0)) + 1, -1, dtype=np.int64)
+            pos[rows] = np.arange(n)
+            li, lj = pos[pi], pos[pj]
+            ok = (li >= 0) & (lj >= 0)
+            li, lj = li[ok], lj[ok]
+        else:
+            # any other VS (e.g. the reference's FaissVS): the reference's own relation — every row against every row of the
+            # frame through vs(..., K=n, ids=rows) (sem_dedup.py:45 via sem_sim_join.py:132-134), `_scores > threshold` (:46)
+            qv = vs.get_vectors_from_index(col_index_dir, rows.tolist())
+            out = vs(qv, n, ids=rows.tolist())
+            sc = np.asarray(out.distances, dtype=np.float32).reshape(n, -1)
+            ix = np.asarray([list(r) for r in out.indices], dtype=np.int64).reshape(n, -1)
+            pos = np.full(int(rows.max()) + 1, -1, dtype=np.int64)
+            pos[rows] = np.arange(n)
+            qi, slot = np.nonzero((sc > threshold) & (ix >= 0))
+            li, lj = qi.astype(np.int64), pos[ix[qi, slot]]
+        # nodes are distinct text values, numbered in order of first appearance (sem_dedup.py:47,51-56); a missing value
+        # (None / NaN, factorize code -1) never equals anything in the reference's `!=` / set logic either: it joins nothing
         codes, uniques = pd.factorize(self._obj[col_name], sort=False)
         ci, cj = codes[li], codes[lj]
-        diff = ci != cj
+        diff = (ci != cj) & (ci >= 0) & (cj >= 0)
         ci, cj = ci[diff], cj[diff]
-        labels = nv.connected_components(len(uniques), ci, cj, getattr(vs, "device", 0))
+        if len(uniques) == 0 or len(ci) == 0:
+            return self._obj
+        labels = nv.connected_components(len(uniques), ci, cj, getattr(vs, "device", 0))  # device union-find
         removed_codes = np.nonzero(labels != np.arange(len(uniques)))[0]
         removed_vals = uniques[removed_codes]
         return self._obj[~self._obj[col_name].isin(removed_vals)]

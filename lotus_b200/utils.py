@@ -24,9 +24,15 @@ def cluster(col_name: str, ncentroids: int) -> Callable[..., list[int]]:
         if vs.index_dir != col_index_dir:
             vs.load_index(col_index_dir)
         assert vs.index_dir == col_index_dir
-        if not hasattr(vs, "kmeans"):
-            raise ValueError("sem_cluster_by needs a vector store with kmeans (B200VS)")
         ids = df.index.tolist()  # assumes df index hasn't been reset and corresponds to index positions (utils.py:58)
+        if not hasattr(vs, "kmeans"):
+            # some other VS (e.g. the reference's FaissVS): the reference's own code path, faiss included (utils.py:32,59-70)
+            import faiss  # type: ignore
+            vec_set = vs.get_vectors_from_index(col_index_dir, ids)
+            km = faiss.Kmeans(vec_set.shape[1], ncentroids, niter=niter, verbose=verbose)
+            km.train(vec_set)
+            _scores, indices = km.index.search(vec_set, 1)
+            return indices.flatten()
         assign, _centroids, obj = vs.kmeans(ids, ncentroids, niter=niter)
         if verbose:
             for it, o in enumerate(obj):

@@ -67,27 +67,21 @@ def _cuda_tensor(a: Any):
 
 
 class BF16Backed(np.ndarray):
-    """float32 matrix whose values are known to be bfloat16-representable, carrying the bf16 bit patterns alongside.
-    `B200VS.get_vectors_from_index` returns it for bf16 indexes; when the operator hands it back as query vectors
-    (sem_sim_join.py:112-118 -> :130-134) `B200VS.__call__` ships the 2-byte patterns and searches with the exact-operand
-    error bound instead of the fp32-query one. Any slicing / arithmetic drops the tag (plain float32 semantics)."""
-    bf16_bits = None
-
-    def __array_finalize__(self, obj):
-        self.bf16_bits = None
+    """float32 matrix handed out by `B200VS.get_vectors_from_index` for bf16 indexes. It is a plain float32 array to every
+    caller; the name only records where it came from. (Round 1 carried the bf16 bit patterns along as an attribute; an
+    in-place edit such as `q /= norm` left them stale. `B200VS.__call__` now re-derives the 2-byte form from the VALUES —
+    see `_to_host_matrix(exact_bf16_ok=True)` — so nothing can go stale.)"""
 
     @staticmethod
-    def wrap(f32: np.ndarray, bits: np.ndarray) -> "BF16Backed":
-        out = np.ascontiguousarray(f32, dtype=np.float32).view(BF16Backed)
-        out.bf16_bits = bits
-        return out
+    def wrap(f32: np.ndarray, bits: "np.ndarray | None" = None) -> "BF16Backed":
+        return np.ascontiguousarray(f32, dtype=np.float32).view(BF16Backed)
 
 
-def _to_host_matrix(a: Any, want_bf16: bool):
-    """-> (array for the C-ABI, native dtype code, float32 view of the stored values)."""
-    bits = getattr(a, "bf16_bits", None)
-    if isinstance(a, BF16Backed) and bits is not None and bits.shape == a.shape and bits.dtype == np.uint16:
-        return np.ascontiguousarray(bits), nv.BF16, np.asarray(a)
+def _to_host_matrix(a: Any, want_bf16: bool, exact_bf16_ok: bool = False):
+    """-> (array for the C-ABI, native dtype code, float32 view of the stored values).
+    exact_bf16_ok: when every float32 value is bfloat16-representable (e.g. vectors fetched from a bf16 index,
+    sem_sim_join.py:112-118 -> :130-134) ship the exact 2-byte patterns instead: half the H2D bytes and the exact-operand
+    error bound in the certificate. Decided from the values themselves on every call (one threaded host pass)."""
     try:
         import torch
         if isinstance(a, torch.Tensor):
@@ -95,8 +89,7 @@ def _to_host_matrix(a: Any, want_bf16: bool):
             if t.dtype == torch.bfloat16 or want_bf16:
                 bits = t.to(torch.bfloat16).contiguous().cpu().view(torch.int16).numpy().view(np.uint16)
                 return bits, nv.BF16, nv.bf16_bits_to_f32(bits)
-            f = t.to(torch.float32).contiguous().cpu().numpy()
-            return f, nv.F32, f
+            a = t.to(torch.float32).contiguous().cpu().numpy()
     except ImportError:  # pragma: no cover
         pass
     f = np.ascontiguousarray(np.asarray(a), dtype=np.float32)  # faiss casts whatever it is given to float32
@@ -105,6 +98,10 @@ def _to_host_matrix(a: Any, want_bf16: bool):
     if want_bf16:
         bits = nv.f32_to_bf16_bits(f)
         return bits, nv.BF16, nv.bf16_bits_to_f32(bits)
+    if exact_bf16_ok and f.size:
+        bits, exact = nv.f32_to_bf16_checked(f)
+        if exact:
+            return bits, nv.BF16, f
     return f, nv.F32, f
 
 
@@ -135,7 +132,7 @@ class B200VS(VS):
         self.b2_index: nv.Index | None = None
         self.vecs: Any = None
         self._cache: "OrderedDict[str, tuple[float, nv.Index, Any]]" = OrderedDict()
-        self._cache_size = cache_size
+        self._cache_size = max(2, cache_size)
 
     # -- index lifetime ---------------------------------------------------------------------------------------------
     def _build(self, embeddings: Any) -> nv.Index:
@@ -198,14 +195,28 @@ class B200VS(VS):
         self._remember(index_dir, idx, vecs)
 
     # -- queries ----------------------------------------------------------------------------------------------------
+    def _entry_for(self, index_dir: str) -> nv.Index:
+        """Device index of `index_dir` WITHOUT making it the loaded one (faiss_vs.py:38-41 only reads the `vecs` pickle and
+        leaves `self.faiss_index` / `self.index_dir` alone)."""
+        key = os.path.abspath(index_dir)
+        if self.index_dir is not None and self.b2_index is not None and os.path.abspath(self.index_dir) == key:
+            return self.b2_index
+        keep = (self.index_dir, self.b2_index, self.vecs)
+        if self.index_dir is not None and os.path.abspath(self.index_dir) in self._cache:
+            self._cache.move_to_end(os.path.abspath(self.index_dir))  # the loaded index must not be the eviction victim
+        try:
+            self.load_index(index_dir)  # per-directory cache hit, or build + cache the device copy ...
+            return self.b2_index  # type: ignore[return-value]
+        finally:
+            self.index_dir, self.b2_index, self.vecs = keep  # ... but the loaded index stays what it was
+
     def get_vectors_from_index(self, index_dir: str, ids: Any) -> np.ndarray:
-        """faiss_vs.py:38-41 (`pickle.load(vecs)[ids]`), served by the device row-gather kernel."""
-        if self.index_dir is None or os.path.abspath(index_dir) != os.path.abspath(self.index_dir):
-            self.load_index(index_dir)
-        assert self.b2_index is not None
+        """faiss_vs.py:38-41 (`pickle.load(vecs)[ids]`), served by the device row-gather kernel. Like the reference it does
+        not change which index is loaded."""
+        idx = self._entry_for(index_dir)
         ids_a = np.asarray(list(ids) if not isinstance(ids, np.ndarray) else ids, dtype=np.int64)
-        out = self.b2_index.gather(ids_a)
-        return BF16Backed.wrap(nv.bf16_bits_to_f32(out), out) if self.b2_index.dtype == nv.BF16 else out
+        out = idx.gather(ids_a)
+        return BF16Backed.wrap(nv.bf16_bits_to_f32(out)) if idx.dtype == nv.BF16 else out
 
     def __call__(self, query_vectors: Any, K: int, ids: list[int] | None = None, **kwargs: Any) -> RMOutput:
         """faiss_vs.py:43-77. Returns float32 distances [Q,K] and int64 indices [Q,K] (global ids; -1 = no result).
@@ -216,7 +227,7 @@ class B200VS(VS):
         t = _cuda_tensor(query_vectors)
         if t is not None and ids_a is None and t.dim() == 2 and t.device.index == self.device:
             return self._call_device(t, int(K))
-        q, code, _ = _to_host_matrix(query_vectors, False)
+        q, code, _ = _to_host_matrix(query_vectors, False, exact_bf16_ok=self.b2_index.dtype == nv.BF16)
         if q.shape[1] != self.b2_index.d:
             raise ValueError(f"query dimension {q.shape[1]} does not match the index dimension {self.b2_index.d}")
         try:

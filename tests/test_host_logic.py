@@ -293,19 +293,44 @@ def test_sim_join_hands_label_arrays_to_stores_that_take_them(env):
     pd.testing.assert_frame_equal(got, want)
 
 
-def test_bf16_backed_query_matrix_keeps_its_bit_patterns_only_while_untouched():
+def test_bf16_exact_queries_ship_two_byte_patterns_decided_from_the_values():
+    """ADVICE r1 (vs.py:76): the bf16 form of a query batch is derived from its VALUES on every call, never from a tag
+    that an in-place edit could leave stale."""
     from lotus_b200 import _native as nv
     from lotus_b200.vs import BF16Backed, _to_host_matrix
     bits = nv.f32_to_bf16_bits(gauss(6, 16, 3))
-    m = BF16Backed.wrap(nv.bf16_bits_to_f32(bits), bits)
+    m = BF16Backed.wrap(nv.bf16_bits_to_f32(bits))
     assert isinstance(m, np.ndarray) and m.dtype == np.float32
     # handed back untouched (what sem_sim_join does via rm.convert_query_to_query_vector): 2-byte patterns, bf16 dtype code
-    out, code, f32 = _to_host_matrix(lotus.HashRM(dim=16).convert_query_to_query_vector(m), False)
+    out, code, f32 = _to_host_matrix(lotus.HashRM(dim=16).convert_query_to_query_vector(m), False, exact_bf16_ok=True)
     assert code == nv.BF16 and out.dtype == np.uint16 and np.array_equal(out, bits) and np.array_equal(f32, np.asarray(m))
-    # any derived array is a plain float32 matrix again
-    for derived in (m[1:4], m * 2.0, m.copy(), np.ascontiguousarray(m[::2])):
-        out, code, _ = _to_host_matrix(derived, False)
-        assert code == nv.F32 and out.dtype == np.float32
+    # in-place edits that stay bf16-representable ship the NEW values; anything else goes as float32
+    m *= 2.0
+    out, code, _ = _to_host_matrix(m, False, exact_bf16_ok=True)
+    assert code == nv.BF16 and np.array_equal(nv.bf16_bits_to_f32(out), np.asarray(m))
+    m[0, 0] = np.float32(1.0) + np.float32(2.0 ** -20)
+    out, code, _ = _to_host_matrix(m, False, exact_bf16_ok=True)
+    assert code == nv.F32 and out.dtype == np.float32 and np.array_equal(out, np.asarray(m))
+    # without the store asking for it (fp32 index) nothing is converted
+    out, code, _ = _to_host_matrix(m * 0 + 1, False)
+    assert code == nv.F32
+
+
+def test_f32_to_bf16_rounding_matches_the_reference_formula_and_keeps_nan():
+    from lotus_b200 import _native as nv
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal(100_000).astype(np.float32) * np.float32(10.0) ** rng.integers(-20, 20, 100_000).astype(np.float32)
+    a[:8] = [0.0, -0.0, np.inf, -np.inf, 1.0, np.float32(1.0) + np.float32(2.0 ** -8), np.float32(1.0) + np.float32(3 * 2.0 ** -9), 65504.0]
+    u = a.view(np.uint32).astype(np.uint64)
+    want = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
+    got, exact = nv.f32_to_bf16_checked(a)
+    assert np.array_equal(got, want) and not exact
+    assert np.array_equal(oracle.f32_to_bf16_bits(a), got)
+    # NaN payloads must stay NaN (ADVICE r1, _native.py:118: 0x7fffffff used to become -0.0)
+    nan = np.array([0x7fffffff, 0xffffffff, 0x7fc00000, 0x7f800001], dtype=np.uint32).view(np.float32)
+    nb = nv.f32_to_bf16_bits(nan)
+    assert np.isnan(nv.bf16_bits_to_f32(nb)).all()
+    assert nv.f32_to_bf16_checked(nv.bf16_bits_to_f32(got))[1] is True
 
 
 def test_quickstart_example_runs_against_the_test_double(monkeypatch, capsys):

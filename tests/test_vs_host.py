@@ -156,24 +156,61 @@ def test_bf16_store_rounds_once_and_hands_query_bits_back(fake_native, tmp_path)
     assert vs.b2_index.calls[-1][:2] == (np.dtype(np.uint16), nv.BF16)
     D, I = oracle.knn(xb, xb[[1, 5, 9]], 4, oracle.IP)
     assert np.array_equal(out.indices, I) and np.array_equal(out.distances, D)
-    vs(np.asarray(got) * 1.0, 4)                                                     # any derived matrix: plain fp32 queries
+    vs(np.asarray(got) * np.float32(1.0 + 2.0 ** -12), 4)                            # values no longer bf16-exact: plain fp32 queries
     assert vs.b2_index.calls[-1][:2] == (np.dtype(np.float32), nv.F32)
 
 
 def test_install_configures_whichever_settings_object_the_operators_read(fake_native, monkeypatch):
     import sys
     import types
+    import pandas as pd
     try:
         store = lotus.install(dtype="bf16")              # no `lotus` package in this image: our own settings
         assert isinstance(store, B200VS) and lotus.settings.vs is store and store.dtype == "bf16"
     finally:
         lotus.settings.configure(vs=None)
-    # with the real package importable, ITS settings and ITS utils.cluster are the ones the reference operators consult
+    # with the real package importable, ITS settings and ITS utils.cluster are the ones the reference operators consult,
+    # and importing it registers ITS accessors (lotus/sem_ops/*.py) — install() must put ours back AFTER that import
     seen = {}
+
+    class RefDedup:  # what `import lotus` leaves registered under df.sem_dedup
+        def __init__(self, obj):
+            pass
+
     fake = types.ModuleType("lotus")
+    fake.__path__ = []
     fake.settings = types.SimpleNamespace(configure=lambda **kw: seen.update(kw), rm=None, vs=None, enable_cache=False, lm=None)
-    fake.utils = types.SimpleNamespace(cluster="the faiss one")
+    futils = types.ModuleType("lotus.utils")
+    futils.cluster = "the faiss one"
+    fake.utils = futils
     monkeypatch.setitem(sys.modules, "lotus", fake)
+    monkeypatch.setitem(sys.modules, "lotus.utils", futils)
+    pd.api.extensions.register_dataframe_accessor("sem_dedup")(RefDedup)
+    assert type(pd.DataFrame({"a": [1]}).sem_dedup) is RefDedup
     mine = B200VS()
-    assert lotus.install(mine) is mine and seen == {"vs": mine} and fake.utils.cluster is lotus.utils.cluster
+    assert lotus.install(mine) is mine and seen == {"vs": mine} and futils.cluster is lotus.utils.cluster
     assert lotus.settings.vs is None
+    from lotus_b200.sem_ops import SemDedupByDataframe, SemSearchDataframe
+    df = pd.DataFrame({"a": [1]})
+    assert type(df.sem_dedup) is SemDedupByDataframe and type(df.sem_search) is SemSearchDataframe
+
+
+def test_get_vectors_from_index_does_not_switch_the_loaded_index(fake_native, tmp_path):
+    """ADVICE r1 (vs.py:204): the reference only reads the `vecs` pickle (faiss_vs.py:38-41); the loaded index stays."""
+    xa, xb = gauss(12, 8, 21), gauss(9, 8, 22)
+    vs = B200VS()
+    da, db = str(tmp_path / "a"), str(tmp_path / "b")
+    vs.index(None, xb, db)
+    vs.index(None, xa, da)
+    loaded = vs.b2_index
+    got = vs.get_vectors_from_index(db, [3, 0])
+    assert np.array_equal(got, xb[[3, 0]])
+    assert vs.index_dir == da and vs.b2_index is loaded and np.array_equal(vs.vecs, xa)
+    out = vs(got, 2)                                     # searches A, like the reference would
+    D, I = oracle.knn(xa, xb[[3, 0]], 2, oracle.IP)
+    assert np.array_equal(out.indices, I) and np.array_equal(out.distances, D)
+    # a directory that is not cached yet is built and cached, still without becoming the loaded one
+    vs2 = B200VS()
+    vs2.load_index(da)
+    assert np.array_equal(vs2.get_vectors_from_index(db, [1]), xb[[1]]) and vs2.index_dir == da
+    assert np.array_equal(vs2(xa[:1], 1).indices, [[0]])
