@@ -141,6 +141,19 @@ B2_API int b2_kmeans(b2_index* idx, const int64_t* ids, int64_t m, int32_t k, in
 B2_API int b2_kmeans_assign(b2_index* idx, const int64_t* ids, int64_t m, const float* centroids, int32_t k,
                      int64_t* out_assign, float* out_dist);
 
+/* DEVICE-buffer forms for the row-sharded multi-GPU Lloyd loop (lotus_b200/distributed.py sharded_kmeans): nothing visits
+ * the host between the assignment, the per-shard sums and the NCCL all-reduce of [k,d] sums + [k] counts.
+ * b2_kmeans_assign_dev: assign_dev[m] int64 (and dist_dev[m] float32 when non-NULL: the canonical distance to the winner)
+ * for the rows ids_dev[0..m) (NULL = all rows) against centroids_dev[k,d] float32.
+ * b2_kmeans_accumulate_dev: sums_dev[k,d] float32 = per-centroid sums of the member rows in point order (NOT divided),
+ * counts_dev[k] float32; when obj_dev is non-NULL, *obj_dev += sum of squared distances of the rows to
+ * centroids_dev[assign] (float64; centroids_dev = the centroids the assignment was made against).
+ * All pointers live on the index's device; both calls enqueue on `stream` and synchronise it before returning. */
+B2_API int b2_kmeans_assign_dev(b2_index* idx, const int64_t* ids_dev, int64_t m, const float* centroids_dev, int32_t k,
+                         int64_t* assign_dev, float* dist_dev, void* stream);
+B2_API int b2_kmeans_accumulate_dev(b2_index* idx, const int64_t* ids_dev, int64_t m, const int64_t* assign_dev, int32_t k,
+                             const float* centroids_dev, float* sums_dev, float* counts_dev, double* obj_dev, void* stream);
+
 /* per-shard centroid update for multi-GPU Lloyd: for the rows ids[0..m) (or all) and their assignment assign[m],
  * out_sums[k,d] float32 = sum of the member rows of each centroid (point order, fp32, NOT divided), out_counts[k] float32.
  * The caller all-reduces sums and counts over the ranks and divides. HOST buffers. (faiss/Clustering.cpp compute_centroids

@@ -20,7 +20,7 @@ SYMBOLS = [
     "b2_abi_version", "b2_last_error", "b2_device_count", "b2_max_k", "b2_index_create", "b2_index_free",
     "b2_index_ntotal", "b2_index_dim", "b2_index_dtype", "b2_index_metric", "b2_index_device", "b2_index_data_dev",
     "b2_index_search", "b2_index_search_dev", "b2_merge_topk_dev", "b2_index_gather", "b2_threshold_pairs",
-    "b2_connected_components", "b2_kmeans", "b2_kmeans_assign", "b2_kmeans_accumulate", "b2_stats", "b2_stats_reset", "b2_last_filter_ms", "b2_host_f32_to_bf16",
+    "b2_connected_components", "b2_kmeans", "b2_kmeans_assign", "b2_kmeans_accumulate", "b2_kmeans_assign_dev", "b2_kmeans_accumulate_dev", "b2_stats", "b2_stats_reset", "b2_last_filter_ms", "b2_host_f32_to_bf16",
 ]
 
 
@@ -76,6 +76,10 @@ def lib() -> ctypes.CDLL:
     L.b2_kmeans_assign.argtypes = [vp, vp, i64, vp, i32, vp, vp]
     L.b2_kmeans_accumulate.restype = c.c_int
     L.b2_kmeans_accumulate.argtypes = [vp, vp, i64, vp, i32, vp, vp]
+    L.b2_kmeans_assign_dev.restype = c.c_int
+    L.b2_kmeans_assign_dev.argtypes = [vp, vp, i64, vp, i32, vp, vp, vp]
+    L.b2_kmeans_accumulate_dev.restype = c.c_int
+    L.b2_kmeans_accumulate_dev.argtypes = [vp, vp, i64, vp, i32, vp, vp, vp, vp, vp]
     L.b2_host_f32_to_bf16.restype = c.c_int
     L.b2_host_f32_to_bf16.argtypes = [vp, i64, vp, c.POINTER(i32)]
     L.b2_stats.restype = c.c_int
@@ -236,12 +240,29 @@ class Index:
         return assign, dist
 
 
+def _index_kmeans_assign_dev(self, centroids_ptr: int, k: int, assign_ptr: int, dist_ptr: int = 0, ids_ptr: int = 0, m: int = 0,
+                             stream: int = 0) -> None:
+    """DEVICE buffers: assign[m] int64 (and dist[m] float32 when dist_ptr) against centroids[k,d] float32."""
+    check(lib().b2_kmeans_assign_dev(self._h, ctypes.c_void_p(ids_ptr) if ids_ptr else None, m, ctypes.c_void_p(centroids_ptr), k,
+                                     ctypes.c_void_p(assign_ptr), ctypes.c_void_p(dist_ptr) if dist_ptr else None,
+                                     ctypes.c_void_p(stream) if stream else None))
+
+
+def _index_kmeans_accumulate_dev(self, assign_ptr: int, k: int, sums_ptr: int, counts_ptr: int, centroids_ptr: int = 0, obj_ptr: int = 0,
+                                 ids_ptr: int = 0, m: int = 0, stream: int = 0) -> None:
+    """DEVICE buffers: per-shard point-order sums[k,d] + counts[k] (float32); *obj += sum of squared distances (float64)."""
+    check(lib().b2_kmeans_accumulate_dev(self._h, ctypes.c_void_p(ids_ptr) if ids_ptr else None, m, ctypes.c_void_p(assign_ptr), k,
+                                         ctypes.c_void_p(centroids_ptr) if centroids_ptr else None, ctypes.c_void_p(sums_ptr),
+                                         ctypes.c_void_p(counts_ptr), ctypes.c_void_p(obj_ptr) if obj_ptr else None,
+                                         ctypes.c_void_p(stream) if stream else None))
+
+
 def pair_owner(i, nparts: int):
     """Rank that owns the pairs (i, j > i) in `threshold_pairs(part=, nparts=)`: 128-row query tiles are dealt to the ranks in
     groups of one tile per SM (148 on B200; B2_PAIR_GROUP overrides) — mirrors launch_pair_filter in knn_filter_sm100.cu."""
     group = int(os.environ.get("B2_PAIR_GROUP", "0")) or 148
     tile = np.asarray(i, dtype=np.int64) // 128
-    if int(os.environ.get("B2_PAIR_2CTA", "0")):  # CTA pairs: the unit is two consecutive query tiles, one unit per pair of SMs
+    if int(os.environ.get("B2_PAIR_2CTA", "1")):  # CTA pairs (default): the unit is two consecutive query tiles, one unit per pair of SMs
         return ((tile // 2) // max(1, group // 2)) % nparts
     return (tile // group) % nparts
 
@@ -257,6 +278,8 @@ def _index_kmeans_accumulate(self, assign, k: int, ids=None):
 
 
 Index.kmeans_accumulate = _index_kmeans_accumulate
+Index.kmeans_assign_dev = _index_kmeans_assign_dev
+Index.kmeans_accumulate_dev = _index_kmeans_accumulate_dev
 
 
 def connected_components(n: int, pi: np.ndarray, pj: np.ndarray, device: int = 0) -> np.ndarray:

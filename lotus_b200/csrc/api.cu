@@ -40,17 +40,7 @@ int build_view(const void* store, int64_t n, int d, int dtype, DevBuf& filt_pad,
     v.dtype = dtype;
     v.filt_dtype = dtype;
     const int align = dtype == B2_F32 ? 4 : 8;  // TMA row pitch must be a multiple of 16 bytes
-    v.split_dp = 0;
-    static const bool f32_split = [] { const char* e = getenv("B2_F32_SPLIT"); return e && atoi(e) != 0; }();
-    if (dtype == B2_F32 && f32_split) {
-        // fp32 index: bf16 hi|lo split operands for the filter (1.5 bf16 passes instead of a TF32 pass at half rate)
-        v.split_dp = (int32_t)round_up(d, 64);
-        v.filt_dtype = B2_BF16;
-        v.filt_pitch = 2 * (int64_t)v.split_dp;
-        B2_TRY(filt_pad.ensure((size_t)std::max<int64_t>(n, 1) * v.filt_pitch * 2));
-        B2_TRY(launch_split_bf16(store, dtype, n, d, filt_pad.p, v.split_dp, st));
-        v.filt = filt_pad.p;
-    } else if (d % align == 0) {
+    if (d % align == 0) {
         v.filt = store;
         v.filt_pitch = d;
     } else {
@@ -127,14 +117,10 @@ int search_core(b2_index* idx, const MatView& X, int metric, const void* q_dev, 
     int dev_sms = 148;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, idx->device);
     const int filt_dtype = X.filt_dtype;
-    const bool split = X.split_dp > 0;
-    const int64_t q_pitch = split ? 2 * (int64_t)X.split_dp : round_up(X.d, filt_dtype == B2_F32 ? 4 : 8);
-    // hi|lo split: q.x - (q_hi.x_hi + q_hi.x_lo + q_lo.x_hi) = q_lo.x_lo + q.(x - x_hi - x_lo) + (q - q_hi - q_lo).x, each term
-    // <= 2^-18 |q||x| (bf16 rounding is 2^-9 relative, applied twice); accumulation runs over 3*split_dp products
-    const float rel_eps = split ? (float)((double)(3 * X.split_dp + 64) * 1.1920929e-7 + 4.0 * 3.814697265625e-6 + 1e-6)
-                                : filter_rel_eps(X.dtype, filt_dtype, q_dtype, X.d);
+    const int64_t q_pitch = round_up(X.d, filt_dtype == B2_F32 ? 4 : 8);
+    const float rel_eps = filter_rel_eps(X.dtype, filt_dtype, q_dtype, X.d);
     // queries that already have the filter's element type and a TMA-compatible pitch are streamed in place
-    const bool q_in_place = !split && q_dtype == filt_dtype && q_pitch == X.d && (reinterpret_cast<uintptr_t>(q_dev) & 15) == 0;
+    const bool q_in_place = q_dtype == filt_dtype && q_pitch == X.d && (reinterpret_cast<uintptr_t>(q_dev) & 15) == 0;
     // bound the candidate workspace: process the queries in chunks
     const int64_t chunk = 1 << 20;
     for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
@@ -150,17 +136,22 @@ int search_core(b2_index* idx, const MatView& X, int metric, const void* q_dev, 
         B2_TRY(idx->cand_id.ensure((size_t)nqc * n_splits * kp * sizeof(int32_t)));
         B2_TRY(idx->cand_thr.ensure((size_t)nqc * n_splits * 2 * sizeof(float)));  // two epilogue sets per split
         B2_TRY(idx->flags.ensure((size_t)nqc * sizeof(int32_t)));
-        B2_TRY(idx->h_flags.ensure((size_t)nqc * sizeof(int32_t)));
-        if (split) B2_TRY(launch_split_bf16(qc, q_dtype, nqc, X.d, idx->q_filt.p, X.split_dp, st));
-        else if (!q_in_place) B2_TRY(launch_prep_queries(qc, q_dtype, nqc, X.d, idx->q_filt.p, filt_dtype, q_pitch, st));
+        B2_TRY(idx->sel.ensure((size_t)(nqc + 1) * sizeof(int32_t)));  // [0] = counter, [1..] = uncertified queries
+        B2_TRY(idx->h_flags.ensure(64));
+        int32_t* sel_count = idx->sel.as<int32_t>();
+        int32_t* sel_list = sel_count + 1;
+        B2_CUDA(cudaMemsetAsync(sel_count, 0, sizeof(int32_t), st));
+        if (!q_in_place) B2_TRY(launch_prep_queries(qc, q_dtype, nqc, X.d, idx->q_filt.p, filt_dtype, q_pitch, st));
         B2_CUDA(cudaEventRecord(idx->ev0, st));
         B2_TRY(launch_knn_filter(X, q_filt, q_pitch, nqc, metric, kp, n_splits, two_cta, idx->cand_score.as<float>(),
-                                 idx->cand_id.as<int32_t>(), idx->cand_thr.as<float>(), idx->device, st, /*top1=*/k == 1));
+                                 idx->cand_id.as<int32_t>(), idx->cand_thr.as<float>(), idx->device, st));
         B2_CUDA(cudaEventRecord(idx->ev1, st));
         B2_TRY(launch_finalize(X, qc, q_dtype, nqc, metric, k, kp, kp / 2, 2 * n_splits, idx->cand_score.as<float>(),
                                idx->cand_id.as<int32_t>(), idx->cand_thr.as<float>(), rel_eps, id_map, id_offset, osc, oid,
-                               idx->flags.as<int32_t>(), st));
-        B2_CUDA(cudaMemcpyAsync(idx->h_flags.p, idx->flags.p, (size_t)nqc * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+                               idx->flags.as<int32_t>(), sel_list, sel_count, st));
+        // the certificate outcome comes back as ONE counter (the failed queries are compacted on the device)
+        int32_t* h_count = reinterpret_cast<int32_t*>(idx->h_flags.p);
+        B2_CUDA(cudaMemcpyAsync(h_count, sel_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         cudaError_t se = cudaStreamSynchronize(st);
         if (se != cudaSuccess) {
             set_error("search pipeline failed on the device: %s", cudaGetErrorString(se));
@@ -170,23 +161,17 @@ int search_core(b2_index* idx, const MatView& X, int metric, const void* q_dev, 
         if (cudaEventElapsedTime(&ms, idx->ev0, idx->ev1) == cudaSuccess)
             idx->last_filter_ms = (idx->last_filter_ms < 0 ? 0.f : idx->last_filter_ms) + ms;
         // exact fallback for the queries the certificate could not cover
-        const int32_t* hf = reinterpret_cast<const int32_t*>(idx->h_flags.p);
-        std::vector<int32_t> sel;
-        for (int64_t i = 0; i < nqc; ++i)
-            if (hf[i]) sel.push_back((int32_t)i);
-        if (!sel.empty()) {
+        const int64_t n_sel = *h_count;
+        if (n_sel > 0) {
             if (k > dense_max_k()) {
                 set_error("internal: fallback with k=%d", k);
                 return B2_ERANGE;
             }
-            g_stats[ST_FALLBACK] += (int64_t)sel.size();
-            B2_TRY(idx->sel.ensure(sel.size() * sizeof(int32_t)));
-            B2_CUDA(cudaMemcpyAsync(idx->sel.p, sel.data(), sel.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-            const int64_t rows = std::min<int64_t>(dense_rows_cap, (int64_t)sel.size());
+            g_stats[ST_FALLBACK] += n_sel;
+            const int64_t rows = std::min<int64_t>(dense_rows_cap, n_sel);
             B2_TRY(idx->dense.ensure((size_t)rows * X.n * sizeof(float)));
-            B2_TRY(launch_dense_topk(X, qc, q_dtype, nqc, idx->sel.as<int32_t>(), (int64_t)sel.size(), metric, k, id_map,
-                                     id_offset, idx->dense.as<float>(), rows, nullptr, osc, oid, st));
-            B2_CUDA(cudaStreamSynchronize(st));  // `sel` (host vector) must outlive the copy
+            B2_TRY(launch_dense_topk(X, qc, q_dtype, nqc, sel_list, n_sel, metric, k, id_map, id_offset, idx->dense.as<float>(), rows,
+                                     nullptr, osc, oid, st));
         }
     }
     return B2_OK;
@@ -292,6 +277,8 @@ void b2_index_free(b2_index* idx) {
                       &idx->ids_dev, &idx->sub_store, &idx->sub_filt, &idx->sub_norm2, &idx->sort_keys};
     for (DevBuf* b : bufs) b->release();
     idx->h_flags.release();
+    km_work_free(idx->km);
+    idx->km = nullptr;
     if (idx->ev0) cudaEventDestroy(idx->ev0);
     if (idx->ev1) cudaEventDestroy(idx->ev1);
     if (idx->stream) cudaStreamDestroy(idx->stream);

@@ -90,11 +90,9 @@ struct MatView {
     int32_t dtype = B2_F32;       // element type of `store`
     int32_t filt_dtype = B2_F32;  // element type of `filt`: B2_BF16 -> kind::f16 MMA, B2_F32 -> kind::tf32 MMA
     int64_t filt_pitch = 0;  // elements
-    // > 0: `filt` is the bf16 hi|lo split of an fp32 matrix, [n, 2*split_dp] (split_dp = d rounded up to a K-block of 64):
-    // columns [0, split_dp) hold bf16(x), columns [split_dp, 2*split_dp) hold bf16(x - bf16(x)). The filter then runs ONE
-    // bf16 GEMM over three K segments q_hi.x_hi + q_hi.x_lo + q_lo.x_hi (1.5x a bf16 pass, operand error ~2^-16).
-    int32_t split_dp = 0;
     float max_norm = 0.f;    // max_j ||x_j|| (upper bound), for the certification margin
+    const float* max_norm_dev = nullptr;  // when set, the kernels read the bound from device memory instead (no host sync:
+                                          // the k-means loop rebuilds its centroid view every iteration)
 };
 
 struct SearchWorkspace;
@@ -106,7 +104,7 @@ int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int
                       int n_splits, bool two_cta, float* cand_score, int32_t* cand_id, float* cand_thr, int device,
                       cudaStream_t stream, bool top1 = false);
 bool filter_use_pair(int64_t nq);
-int filter_choose_splits(int64_t nq, int64_t n, int num_sms, bool two_cta);
+int filter_choose_splits(int64_t nq, int64_t n, int num_sms, bool two_cta, bool top1 = false);
 int launch_pair_filter(const MatView& X, float thr, int part, int nparts, int32_t* pair_i, int32_t* pair_j,
                        unsigned long long* pair_count, unsigned long long cap, int device, cudaStream_t stream);
 
@@ -117,13 +115,14 @@ int launch_row_norms(const void* x, int dtype, int64_t n, int d, float* norm2, f
                      cudaStream_t stream);
 int launch_convert_pad(const void* x, int dtype, int64_t n, int d, void* out, int out_dtype, int64_t out_pitch,
                        cudaStream_t stream);
-int launch_split_bf16(const void* x, int dtype, int64_t n, int d, void* out, int64_t split_dp, cudaStream_t stream);
+int launch_exact_l2_assigned(const void* pts, int dtype, int64_t m, int d, const float* cent, const int64_t* assign, float* out,
+                             cudaStream_t stream);
 int launch_gather_rows(const void* x, int dtype, int d, const int64_t* ids, int64_t m, int64_t n, void* out,
                        int* err_flag, cudaStream_t stream);
 int launch_finalize(const MatView& X, const void* q, int q_dtype, int64_t nq, int metric, int k, int kp, int list_len,
                     int n_lists, const float* cand_score, const int32_t* cand_id, const float* cand_thr,
                     float rel_eps, const int64_t* id_map, int64_t id_offset, float* out_scores, int64_t* out_idx,
-                    int32_t* flags, cudaStream_t stream);
+                    int32_t* flags, int32_t* sel, int32_t* sel_count, cudaStream_t stream);
 int launch_dense_topk(const MatView& X, const void* q, int q_dtype, int64_t nq, const int32_t* q_sel,
                       int64_t n_sel, int metric, int k, const int64_t* id_map, int64_t id_offset, float* dense_ws,
                       int64_t dense_ws_rows, uint64_t* sort_ws, float* out_scores, int64_t* out_idx, cudaStream_t stream);

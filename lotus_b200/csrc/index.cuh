@@ -58,6 +58,9 @@ struct HostBuf {
     }
 };
 
+struct KmWork;                 // kmeans.cu: per-handle k-means workspaces
+void km_work_free(KmWork* w);  // (defined in kmeans.cu)
+
 struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev) {
@@ -90,6 +93,7 @@ struct b2_index {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_filter_ms = -1.f;
+    b2::KmWork* km = nullptr;
 };
 
 namespace b2 {

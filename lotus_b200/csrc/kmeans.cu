@@ -1,32 +1,76 @@
 // kmeans.cu — sem_cluster_by's core: faiss.Kmeans(d, k, niter).train(x) followed by kmeans.index.search(x, 1)
-// (lotus/utils.py:61-65), restated from faiss/Clustering.cpp exactly as oracle/faiss_flat.c `orc_kmeans` does:
+// (lotus/utils.py:61-65). The algorithm is faiss/Clustering.cpp's, as oracle/faiss_flat.c `orc_kmeans` restates it:
 //   host control flow : subsample to 256*k points with rand_perm(seed) (std::mt19937), initial centroids = first k of
 //                       rand_perm(seed+1), niter Lloyd iterations, split_clusters with RandomGenerator(1234)
-//   assignment        : L2 top-1 of every point against the k centroids through the SAME exact pipeline as search
-//                       (tcgen05 filter -> canonical re-score -> certificate); argmin ties -> lowest centroid id
-//   centroid update   : faiss sums the member points in POINT ORDER in fp32 and scales by 1/count. That order is
-//                       kept: a stable counting sort builds per-centroid member lists in point order, then one thread
-//                       per (centroid, dimension) adds its column sequentially -> bit-identical centroids.
+//   assignment        : argmin_c ||x - c||^2, ties -> lowest centroid id, decided on the canonical (fp64-accumulated) distance
+//   centroid update   : faiss sums the member points in POINT ORDER in fp32 and scales by 1/count -> bit-identical centroids
+//
+// Device pipeline of one Lloyd iteration (everything stays on the device; the only host round trip is one 4-byte counter):
+//   1. centroid view  : bf16 (or tf32) filter copy of the fp32 centroids + canonical squared norms + max norm (device scalar)
+//   2. filter         : knn_filter_kernel<16, L2, ., ., TOP1> — tcgen05 scores of every point against every centroid, the
+//                       epilogue keeps each point's best two centroids and the third-best score in registers
+//   3. km_assign_finalize_kernel (thread per point): winner c1 by filter score, runner-up bound f2 (second best, third-best
+//                       bounds of every list). |filter - exact| <= eps for every centroid, so f1 - f2 > 2 eps (+ fp32 rounding
+//                       slack) PROVES c1 is the exact argmin with no tie: assigned without touching the point again.
+//                       Points that cannot be proven are appended to a device list ...
+//   4. second level   : ... gathered and answered by the general exact pipeline (search_core: KP=16 lists, canonical re-score,
+//                       certificate, dense fallback) and scattered back. Typically < 2 % of the points, ~0 after a few iterations.
+//   5. update         : stable counting sort of the points by centroid (member lists in point order), then one warp per
+//                       (centroid, 16-byte column chunk) adds its members sequentially with 8 row loads in flight; the same pass
+//                       accumulates the objective (sum of exact distances to the OLD centroids, fp64) when it is asked for.
+//   6. km_split_kernel: faiss's split_clusters on the device (one block; a device MT19937 replays RandomGenerator(1234)).
 #include <algorithm>
 #include <chrono>
 #include <random>
+#include <unordered_map>
 #include <vector>
 
 #include "index.cuh"
 
 namespace b2 {
+
+struct KmWork {
+    DevBuf cent[2], cent_filt, cent_norm2, scalar, pts, pts_norm2, train, train_norm2, assign, members, offsets, totals, blk, hassign, ids,
+        obj, flag_ids, flag_count, sub, sub_dis, sub_assign, fin_assign, fin_dis, perm;
+    HostBuf h_count;
+    void release() {
+        DevBuf* all[] = {&cent[0], &cent[1], &cent_filt, &cent_norm2, &scalar, &pts, &pts_norm2, &train, &train_norm2, &assign, &members,
+                         &offsets, &totals, &blk, &hassign, &ids, &obj, &flag_ids, &flag_count, &sub, &sub_dis, &sub_assign, &fin_assign,
+                         &fin_dis, &perm};
+        for (DevBuf* b : all) b->release();
+        h_count.release();
+    }
+};
+
+void km_work_free(KmWork* w) {
+    if (!w) return;
+    w->release();
+    delete w;
+}
+
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 
-// faiss/utils/random.cpp rand_perm: Fisher-Yates with rng.rand_int(n - i) = mt() % (n - i)
-void rand_perm(std::vector<int64_t>& perm, int64_t n, int64_t seed) {
-    perm.resize(n);
-    for (int64_t i = 0; i < n; ++i) perm[i] = i;
+// First `take` entries of faiss/utils/random.cpp rand_perm(n, seed): Fisher-Yates with rng.rand_int(n - i) = mt() % (n - i).
+// Entry i is final after step i, so only `take` steps are replayed, over a sparse view of the (otherwise identity) array.
+void rand_perm_prefix(std::vector<int64_t>& out, int64_t n, int64_t take, int64_t seed) {
+    out.resize(take);
     std::mt19937 mt((unsigned int)seed);
-    for (int64_t i = 0; i + 1 < n; ++i) {
-        const int64_t i2 = i + (int64_t)(mt() % (uint32_t)(n - i));
-        std::swap(perm[i], perm[i2]);
+    std::unordered_map<int64_t, int64_t> moved;
+    moved.reserve((size_t)take * 2);
+    auto at = [&](int64_t i) {
+        auto it = moved.find(i);
+        return it == moved.end() ? i : it->second;
+    };
+    for (int64_t i = 0; i < take; ++i) {
+        if (i + 1 < n) {
+            const int64_t i2 = i + (int64_t)(mt() % (uint32_t)(n - i));
+            const int64_t a = at(i), b = at(i2);
+            moved[i] = b;
+            moved[i2] = a;
+        }
+        out[i] = at(i);
     }
 }
 
@@ -41,15 +85,50 @@ __global__ void rows_to_f32_kernel(const void* x, int dtype, int d, const int64_
     }
 }
 
-__global__ void sum_f32_kernel(const float* v, int64_t n, double* out) {
-    double acc = 0.0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += (double)v[i];
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
-    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+// ---- step 3: decide the assignment from the filter's top-2 lists ---------------------------------------------------------
+// cand_* hold, per point and per list (2 epilogue sets x n_splits), the best two (score, centroid) pairs in slots 0-1 and the
+// third-best score in cand_thr (-inf when the list saw fewer than three centroids). score = 2 x.c - ||c||^2 (larger = nearer).
+__global__ void km_assign_finalize_kernel(const float* cand_score, const int32_t* cand_id, const float* cand_thr, int64_t m, int n_lists,
+                                          int list_len, const float* pnorm2, const float* max_norm_dev, float rel_eps, int64_t* assign,
+                                          int64_t* flag_ids, int32_t* flag_count, int64_t base) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    float f1 = -INFINITY, f2 = -INFINITY;
+    int32_t c1 = -1;
+    for (int l = 0; l < n_lists; ++l) {
+        const size_t off = ((size_t)i * n_lists + l) * list_len;
+        const float2 s = *reinterpret_cast<const float2*>(cand_score + off);
+        const int2 id = *reinterpret_cast<const int2*>(cand_id + off);
+        if (id.x >= 0) {
+            if (s.x > f1) {
+                f2 = f1;
+                f1 = s.x;
+                c1 = id.x;
+            } else {
+                f2 = fmaxf(f2, s.x);  // an equal score is a potential tie: it closes the gap to zero
+            }
+        }
+        if (id.y >= 0) f2 = fmaxf(f2, s.y);
+        f2 = fmaxf(f2, cand_thr[(size_t)i * n_lists + l]);
+    }
+    const double mx = (double)__ldg(max_norm_dev);
+    const double qn2 = (double)pnorm2[base + i];
+    const double qn = sqrt(qn2);
+    // |filter score - exact score| for any centroid (same bound as finalize_kernel's L2 certificate)
+    const double eps_s = 2.0 * (double)rel_eps * qn * mx + 2.4e-7 * (mx * mx + 2.0 * qn * mx) + 1e-30;
+    // the reported distances are fp32 roundings of ||x||^2 - score: two exact scores further apart than this cannot round equal
+    const double slack = 2.4e-7 * (qn2 + fmax(fabs((double)f1), fabs((double)f2)));
+    const bool certain = c1 >= 0 && ((double)f1 - (double)f2) > 2.0 * eps_s + slack;  // false for NaN scores as well
+    assign[base + i] = c1;
+    if (!certain) flag_ids[atomicAdd(flag_count, 1)] = base + i;
 }
 
-// ---- stable counting sort of points by centroid (member lists in point order) ---------------------------------------
+__global__ void km_scatter_kernel(const int64_t* flag_ids, int64_t n, const int64_t* sub_assign, int64_t* assign) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j < n) assign[flag_ids[j]] = sub_assign[j];
+}
+
+// ---- step 5a: stable counting sort of points by centroid (member lists in point order) --------------------------------
 // block b (ONE warp) owns the contiguous point range [b*L, (b+1)*L)
 __global__ void km_count_kernel(const int64_t* assign, int64_t n, int64_t L, int k, int32_t* cnt) {
     extern __shared__ int32_t s_cnt[];
@@ -66,6 +145,7 @@ __global__ void km_scan_blocks_kernel(int32_t* cnt, int nb, int k, int32_t* tota
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= k) return;
     int32_t run = 0;
+#pragma unroll 8
     for (int b = 0; b < nb; ++b) {
         const int32_t t = cnt[(size_t)b * k + c];
         cnt[(size_t)b * k + c] = run;
@@ -74,15 +154,32 @@ __global__ void km_scan_blocks_kernel(int32_t* cnt, int nb, int k, int32_t* tota
     totals[c] = run;
 }
 
+// offsets[c] = sum of totals[0..c): one block, warp-shuffle scan over chunks of 1024 centroids
 __global__ void km_scan_totals_kernel(const int32_t* totals, int k, int64_t* offsets) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        int64_t run = 0;
-        for (int c = 0; c < k; ++c) {
-            offsets[c] = run;
-            run += totals[c];
+    __shared__ int64_t s_warp[32];
+    __shared__ int64_t s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < k; c0 += 1024) {
+        const int c = c0 + threadIdx.x;
+        const int64_t v = c < k ? (int64_t)totals[c] : 0;
+        int64_t incl = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int64_t o = __shfl_up_sync(FULL, incl, off);
+            if (lane >= off) incl += o;
         }
-        offsets[k] = run;
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int64_t before = s_carry;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        if (c < k) offsets[c] = before + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = before + incl;
+        __syncthreads();
     }
+    if (threadIdx.x == 0) offsets[k] = s_carry;
 }
 
 __global__ void km_fill_kernel(const int64_t* assign, int64_t n, int64_t L, int k, const int32_t* blk_start, const int64_t* offsets,
@@ -109,83 +206,193 @@ __global__ void km_fill_kernel(const int64_t* assign, int64_t n, int64_t L, int 
     }
 }
 
-// thread (c, j): centroid[c][j] = (sum over members of c, in point order, of x[p][j]) * (1 / count)   [all fp32]
+// ---- step 5b: centroid sums in point order ---------------------------------------------------------------------------------
+// One warp per (centroid, chunk of 32 x V columns), lane = V consecutive columns (one 16-byte load per row), U member rows
+// in flight per step; every column is still one sequential fp32 chain over the members in point order, which is what makes
+// the centroids bit-identical to faiss's compute_centroids. With cent_old the same pass accumulates
+// sum_members ||x - c_old||^2 in fp64 (the iteration's objective).
+template <bool BF16>
+__global__ void __launch_bounds__(1024) km_accumulate_vec_kernel(const void* x, int d, const int64_t* ids, const int32_t* members,
+                                                                 const int64_t* offsets, const float* cent_old, float* cent_out,
+                                                                 float* hassign, double* obj, int normalize) {
+    constexpr int V = BF16 ? 8 : 4;
+    constexpr int U = 8;
+    const int c = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int vec = threadIdx.x;  // index of this lane's 16-byte column group inside a row
+    const int col0 = vec * V;
+    const bool active = col0 < d;
+    const int64_t o0 = offsets[c], o1 = offsets[c + 1];
+    const float cntf = (float)(o1 - o0);
+    if (threadIdx.x == 0) hassign[c] = cntf;
+    const size_t row_vecs = (size_t)d / V;
+    const uint4* xv = reinterpret_cast<const uint4*>(x);
+    float acc[V], cold[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        acc[j] = 0.f;
+        cold[j] = (cent_old && active) ? cent_old[(size_t)c * d + col0 + j] : 0.f;
+    }
+    double dsum = 0.0;
+    const bool want_obj = cent_old != nullptr;
+    auto consume = [&](const uint4& raw) {
+        float v[V];
+        if constexpr (BF16) {
+            v[0] = __uint_as_float(raw.x << 16); v[1] = __uint_as_float(raw.x & 0xffff0000u);
+            v[2] = __uint_as_float(raw.y << 16); v[3] = __uint_as_float(raw.y & 0xffff0000u);
+            v[4] = __uint_as_float(raw.z << 16); v[5] = __uint_as_float(raw.z & 0xffff0000u);
+            v[6] = __uint_as_float(raw.w << 16); v[7] = __uint_as_float(raw.w & 0xffff0000u);
+        } else {
+            v[0] = __uint_as_float(raw.x); v[1] = __uint_as_float(raw.y); v[2] = __uint_as_float(raw.z); v[3] = __uint_as_float(raw.w);
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] = __fadd_rn(acc[j], v[j]);
+        if (want_obj) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const double df = (double)v[j] - (double)cold[j];
+                dsum = fma(df, df, dsum);
+            }
+        }
+    };
+    int64_t o = o0;
+    for (; o + U <= o1; o += U) {
+        uint4 raw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t p = members[o + u];  // warp-uniform address
+            const int64_t r = ids ? ids[p] : p;
+            raw[u] = active ? __ldg(xv + (size_t)r * row_vecs + vec) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) consume(raw[u]);
+    }
+    for (; o < o1; ++o) {
+        const int64_t p = members[o];
+        const int64_t r = ids ? ids[p] : p;
+        const uint4 raw = active ? __ldg(xv + (size_t)r * row_vecs + vec) : make_uint4(0, 0, 0, 0);
+        consume(raw);
+    }
+    if (active) {
+        float norm = 1.f;
+        if (normalize && o1 > o0) norm = __fdiv_rn(1.0f, cntf);
+#pragma unroll
+        for (int j = 0; j < V; ++j) cent_out[(size_t)c * d + col0 + j] = (normalize && o1 > o0) ? __fmul_rn(acc[j], norm) : acc[j];
+    }
+    if (want_obj) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) dsum += __shfl_xor_sync(FULL, dsum, off);
+        if (lane == 0 && dsum != 0.0) atomicAdd(obj, dsum);
+    }
+}
+
+// generic shapes (row size not a multiple of 16 bytes): thread (c, j) sums column j over the members in point order
 __global__ void km_accumulate_kernel(const void* x, int dtype, int d, const int64_t* ids, const int32_t* members,
-                                     const int64_t* offsets, float* centroids, float* hassign, int normalize) {
+                                     const int64_t* offsets, const float* cent_old, float* cent_out, float* hassign, double* obj,
+                                     int normalize) {
     const int c = blockIdx.x;
     const int64_t o0 = offsets[c], o1 = offsets[c + 1];
     const float cntf = (float)(o1 - o0);
     if (threadIdx.x == 0 && blockIdx.y == 0) hassign[c] = cntf;
     const int j = blockIdx.y * blockDim.x + threadIdx.x;
-    if (j >= d) return;
+    const bool active = j < d;
     float acc = 0.f;
-    int64_t o = o0;
-    for (; o + 4 <= o1; o += 4) {
-        float v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int64_t p = members[o + u];
+    double dsum = 0.0;
+    const float cold = (cent_old && active) ? cent_old[(size_t)c * d + j] : 0.f;
+    if (active) {
+        for (int64_t o = o0; o < o1; ++o) {
+            const int64_t p = members[o];
             const int64_t r = ids ? ids[p] : p;
-            v[u] = dtype == B2_F32 ? reinterpret_cast<const float*>(x)[r * d + j]
-                                   : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[r * d + j]);
+            const float v = dtype == B2_F32 ? reinterpret_cast<const float*>(x)[r * d + j]
+                                            : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[r * d + j]);
+            acc = __fadd_rn(acc, v);
+            if (cent_old) {
+                const double df = (double)v - (double)cold;
+                dsum = fma(df, df, dsum);
+            }
         }
+        if (normalize && o1 > o0) acc = __fmul_rn(acc, __fdiv_rn(1.0f, cntf));
+        cent_out[(size_t)c * d + j] = acc;
+    }
+    if (cent_old) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc = __fadd_rn(acc, v[u]);
+        for (int off = 16; off >= 1; off >>= 1) dsum += __shfl_xor_sync(FULL, dsum, off);
+        if ((threadIdx.x & 31) == 0 && dsum != 0.0) atomicAdd(obj, dsum);
     }
-    for (; o < o1; ++o) {
-        const int64_t p = members[o];
-        const int64_t r = ids ? ids[p] : p;
-        const float v = dtype == B2_F32 ? reinterpret_cast<const float*>(x)[r * d + j]
-                                        : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[r * d + j]);
-        acc = __fadd_rn(acc, v);
-    }
-    if (normalize && o1 > o0) {
-        const float norm = __fdiv_rn(1.0f, cntf);
-        acc = __fmul_rn(acc, norm);
-    }
-    centroids[(size_t)c * d + j] = acc;
 }
 
-// faiss/Clustering.cpp split_clusters on the host copy (EPS = 1/1024, RandomGenerator rng(1234))
-int split_clusters_host(int d, int k, int64_t n, std::vector<float>& hassign, std::vector<float>& centroids) {
-    const double EPS = 1 / 1024.;
-    int nsplit = 0;
-    std::mt19937 mt(1234u);
-    for (int ci = 0; ci < k; ci++) {
-        if (hassign[ci] == 0) {
-            int cj;
-            for (cj = 0; true; cj = (cj + 1) % k) {
-                const float p = (hassign[cj] - 1.0) / (float)(n - k);
-                const float r = mt() / float(mt.max());
-                if (r < p) break;
+// ---- step 6: faiss/Clustering.cpp split_clusters (EPS = 1/1024, RandomGenerator rng(1234) = std::mt19937) on the device ----
+// One block. Clusters are visited in order; an empty one takes a copy of a cluster cj drawn with probability proportional to
+// its size (rejection loop over cj = 0, 1, ... with rng.rand_float() = mt() / float(mt.max())), the two copies are perturbed
+// symmetrically and the size is shared. The draws depend on the sizes left by earlier splits, so the walk is sequential;
+// thread 0 draws, the block copies.
+struct DevMt19937 {
+    uint32_t* mt;
+    int idx;
+    __device__ void seed(uint32_t s) {
+        mt[0] = s;
+        for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+        idx = 624;
+    }
+    __device__ uint32_t next() {
+        if (idx >= 624) {
+            for (int i = 0; i < 624; ++i) {
+                const uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+                mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
             }
-            memcpy(centroids.data() + (size_t)ci * d, centroids.data() + (size_t)cj * d, sizeof(float) * d);
-            for (int j = 0; j < d; j++) {
-                if (j % 2 == 0) {
-                    centroids[(size_t)ci * d + j] *= 1 + EPS;
-                    centroids[(size_t)cj * d + j] *= 1 - EPS;
-                } else {
-                    centroids[(size_t)ci * d + j] *= 1 - EPS;
-                    centroids[(size_t)cj * d + j] *= 1 + EPS;
-                }
-            }
-            hassign[ci] = hassign[cj] / 2;
-            hassign[cj] -= hassign[ci];
-            nsplit++;
+            idx = 0;
         }
-    }
-    return nsplit;
-}
-
-struct KmWork {
-    DevBuf cent, cent_filt, cent_norm2, scalar, dis, assign, members, offsets, totals, blk, hassign, ids, train, obj;
-    void release() {
-        DevBuf* all[] = {&cent, &cent_filt, &cent_norm2, &scalar, &dis, &assign, &members, &offsets, &totals, &blk, &hassign, &ids, &train, &obj};
-        for (DevBuf* b : all) b->release();
+        uint32_t y = mt[idx++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
     }
 };
 
-// searchable view of the fp32 centroid matrix; the filter operand matches the point dtype (bf16 points -> bf16 copy)
+__global__ void __launch_bounds__(256) km_split_kernel(int d, int k, int64_t n, float* hassign, float* centroids) {
+    __shared__ uint32_t s_mt[624];
+    __shared__ int s_cj;
+    int any = 0;
+    for (int c = threadIdx.x; c < k; c += blockDim.x) any |= hassign[c] == 0.f;
+    if (!__syncthreads_or(any)) return;
+    DevMt19937 rng{s_mt, 624};
+    if (threadIdx.x == 0) rng.seed(1234u);
+    __syncthreads();
+    const double EPS = 1 / 1024.;
+    for (int ci = 0; ci < k; ++ci) {
+        if (hassign[ci] != 0.f) continue;  // block-uniform (hassign is only written between barriers)
+        if (threadIdx.x == 0) {
+            int cj = 0;
+            for (;; cj = (cj + 1) % k) {
+                // float p = (hassign[cj] - 1.0) / (float)(n - k);  float r = rng.rand_float();
+                const float p = (float)(((double)hassign[cj] - 1.0) / (double)(float)(n - k));
+                const float r = __fdiv_rn(__uint2float_rn(rng.next()), 4294967296.0f);
+                if (r < p) break;
+            }
+            s_cj = cj;
+        }
+        __syncthreads();
+        const int cj = s_cj;
+        for (int j = threadIdx.x; j < d; j += blockDim.x) {
+            const float src = centroids[(size_t)cj * d + j];
+            const double up = 1 + EPS, down = 1 - EPS;
+            centroids[(size_t)ci * d + j] = (float)((double)src * ((j % 2 == 0) ? up : down));
+            centroids[(size_t)cj * d + j] = (float)((double)src * ((j % 2 == 0) ? down : up));
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const float h = hassign[cj] / 2;
+            hassign[ci] = h;
+            hassign[cj] -= h;
+        }
+        __syncthreads();
+    }
+}
+
+// searchable view of the fp32 centroid matrix; the filter operand matches the point dtype (bf16 points -> bf16 copy).
+// No host synchronisation: the max norm stays in device memory (MatView::max_norm_dev).
 int centroid_view(const float* cent, int k, int d, int point_dtype, KmWork& w, MatView& v, cudaStream_t st) {
     v.store = cent;
     v.n = k;
@@ -212,30 +419,93 @@ int centroid_view(const float* cent, int k, int d, int point_dtype, KmWork& w, M
     B2_TRY(w.cent_norm2.ensure((size_t)k * sizeof(float)));
     B2_TRY(w.scalar.ensure(64));
     B2_TRY(launch_row_norms(cent, B2_F32, k, d, w.cent_norm2.as<float>(), w.scalar.as<float>(), st));
-    float mx = 0.f;
-    B2_CUDA(cudaMemcpyAsync(&mx, w.scalar.p, sizeof(float), cudaMemcpyDeviceToHost, st));
-    B2_CUDA(cudaStreamSynchronize(st));
     v.norm2 = w.cent_norm2.as<float>();
-    v.max_norm = mx;
+    v.max_norm = 0.f;
+    v.max_norm_dev = w.scalar.as<float>();
     return B2_OK;
 }
 
-// assign[m], dis[m] for the rows pts[m,d] (device, index dtype) against the centroids
-int assign_points(b2_index* idx, const void* pts, int64_t m, const float* cent, int k, KmWork& w, float* dis, int64_t* assign,
-                  cudaStream_t st) {
+// assign[m] (int64, device) for the rows pts[m,d] (device, index dtype; pnorm2[m] = their canonical squared norms) against
+// the k centroids cent[k,d] (fp32, device). Steps 1-4 of the header.
+int assign_points(b2_index* idx, const void* pts, const float* pnorm2, int64_t m, const float* cent, int k, KmWork& w, int64_t* assign,
+                  cudaStream_t st, int64_t* n_second_level = nullptr) {
+    idx->last_filter_ms = -1.f;
+    if (n_second_level) *n_second_level = 0;
+    if (m <= 0) return B2_OK;
+    const int d = idx->d;
     MatView cv;
-    B2_TRY(centroid_view(cent, k, idx->d, idx->dtype, w, cv, st));
-    return search_core(idx, cv, B2_METRIC_L2, pts, idx->dtype, m, 1, nullptr, 0, dis, assign, st);
+    B2_TRY(centroid_view(cent, k, d, idx->dtype, w, cv, st));
+    int dev_sms = 148;
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, idx->device);
+    const int filt_dtype = cv.filt_dtype;
+    const int kp = 16;
+    const int64_t q_pitch = round_up(d, filt_dtype == B2_F32 ? 4 : 8);
+    const float rel_eps = filter_rel_eps(B2_F32, filt_dtype, idx->dtype, d);
+    const bool q_in_place = idx->dtype == filt_dtype && q_pitch == d && (reinterpret_cast<uintptr_t>(pts) & 15) == 0;
+    B2_TRY(w.flag_ids.ensure((size_t)m * sizeof(int64_t)));
+    B2_TRY(w.flag_count.ensure(64));
+    B2_TRY(w.h_count.ensure(64));
+    B2_CUDA(cudaMemsetAsync(w.flag_count.p, 0, sizeof(int32_t), st));
+    const int64_t chunk = (int64_t)1 << 23;
+    B2_CUDA(cudaEventRecord(idx->ev0, st));
+    for (int64_t q0 = 0; q0 < m; q0 += chunk) {
+        const int64_t mc = std::min<int64_t>(chunk, m - q0);
+        const char* pc = reinterpret_cast<const char*>(pts) + (size_t)q0 * d * esize(idx->dtype);
+        const bool two_cta = filter_use_pair(mc);
+        const int n_splits = filter_choose_splits(mc, k, dev_sms, two_cta, /*top1=*/true);
+        if (!q_in_place) {
+            B2_TRY(idx->q_filt.ensure((size_t)mc * q_pitch * esize(filt_dtype)));
+            B2_TRY(launch_prep_queries(pc, idx->dtype, mc, d, idx->q_filt.p, filt_dtype, q_pitch, st));
+        }
+        const void* q_filt = q_in_place ? static_cast<const void*>(pc) : idx->q_filt.p;
+        B2_TRY(idx->cand_score.ensure((size_t)mc * n_splits * kp * sizeof(float)));
+        B2_TRY(idx->cand_id.ensure((size_t)mc * n_splits * kp * sizeof(int32_t)));
+        B2_TRY(idx->cand_thr.ensure((size_t)mc * n_splits * 2 * sizeof(float)));
+        B2_TRY(launch_knn_filter(cv, q_filt, q_pitch, mc, B2_METRIC_L2, kp, n_splits, two_cta, idx->cand_score.as<float>(),
+                                 idx->cand_id.as<int32_t>(), idx->cand_thr.as<float>(), idx->device, st, /*top1=*/true));
+        if (q0 + chunk >= m) B2_CUDA(cudaEventRecord(idx->ev1, st));
+        km_assign_finalize_kernel<<<(unsigned)ceil_div(mc, 256), 256, 0, st>>>(
+            idx->cand_score.as<float>(), idx->cand_id.as<int32_t>(), idx->cand_thr.as<float>(), mc, 2 * n_splits, kp / 2, pnorm2,
+            cv.max_norm_dev, rel_eps, assign, w.flag_ids.as<int64_t>(), w.flag_count.as<int32_t>(), q0);
+        B2_LAUNCH_CHECK();
+    }
+    int32_t* h_count = reinterpret_cast<int32_t*>(w.h_count.p);
+    B2_CUDA(cudaMemcpyAsync(h_count, w.flag_count.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    cudaError_t se = cudaStreamSynchronize(st);
+    if (se != cudaSuccess) {
+        set_error("k-means assignment failed on the device: %s", cudaGetErrorString(se));
+        return B2_ECUDA;
+    }
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, idx->ev0, idx->ev1) == cudaSuccess) idx->last_filter_ms = ms;
+    const int64_t nf = *h_count;
+    g_stats[ST_QUERIES] += m - nf;  // (search_core counts the second-level points itself)
+    if (n_second_level) *n_second_level = nf;
+    if (nf > 0) {
+        // points the gap test could not prove: the general exact pipeline on the gathered rows
+        const float filt_ms = idx->last_filter_ms;
+        B2_TRY(w.sub.ensure((size_t)nf * d * esize(idx->dtype)));
+        B2_TRY(w.sub_dis.ensure((size_t)nf * sizeof(float)));
+        B2_TRY(w.sub_assign.ensure((size_t)nf * sizeof(int64_t)));
+        int* err = reinterpret_cast<int*>(w.scalar.as<char>() + 16);
+        B2_TRY(launch_gather_rows(pts, idx->dtype, d, w.flag_ids.as<int64_t>(), nf, m, w.sub.p, err, st));
+        B2_TRY(search_core(idx, cv, B2_METRIC_L2, w.sub.p, idx->dtype, nf, 1, nullptr, 0, w.sub_dis.as<float>(), w.sub_assign.as<int64_t>(), st));
+        km_scatter_kernel<<<(unsigned)ceil_div(nf, 256), 256, 0, st>>>(w.flag_ids.as<int64_t>(), nf, w.sub_assign.as<int64_t>(), assign);
+        B2_LAUNCH_CHECK();
+        idx->last_filter_ms = filt_ms;
+    }
+    return B2_OK;
 }
 
+// Steps 5-6: member lists, centroid sums (into cent_out), optional objective against cent_old, optional split.
 int update_centroids(b2_index* idx, const void* x, const int64_t* row_ids, int64_t n, const int64_t* assign, int k, KmWork& w,
-                     float* cent, cudaStream_t st, int normalize = 1) {
+                     const float* cent_old, float* cent_out, double* obj, cudaStream_t st, int normalize) {
     const int d = idx->d;
-    // one warp per block walks its point range in order; 1024 ranges keep the per-centroid scan over blocks short
+    // one warp per block walks its point range in order; <= 1024 ranges keep the per-centroid scan over blocks short
     int64_t nb = std::min<int64_t>(1024, std::max<int64_t>(1, ceil_div(n, 256)));
     while (nb > 1 && nb * (int64_t)k > ((int64_t)1 << 26)) nb /= 2;
-    const int64_t L = ceil_div(n, nb);
-    nb = ceil_div(n, L);
+    const int64_t L = ceil_div(std::max<int64_t>(n, 1), nb);
+    nb = std::max<int64_t>(1, ceil_div(n, L));
     const size_t smem = (size_t)k * sizeof(int32_t);
     if (smem > 200 * 1024) {
         set_error("k=%d centroids exceed the shared-memory budget of the member-list kernels", k);
@@ -254,24 +524,37 @@ int update_centroids(b2_index* idx, const void* x, const int64_t* row_ids, int64
     B2_LAUNCH_CHECK();
     km_scan_blocks_kernel<<<(unsigned)ceil_div(k, 128), 128, 0, st>>>(w.blk.as<int32_t>(), (int)nb, k, w.totals.as<int32_t>());
     B2_LAUNCH_CHECK();
-    km_scan_totals_kernel<<<1, 32, 0, st>>>(w.totals.as<int32_t>(), k, w.offsets.as<int64_t>());
+    km_scan_totals_kernel<<<1, 1024, 0, st>>>(w.totals.as<int32_t>(), k, w.offsets.as<int64_t>());
     B2_LAUNCH_CHECK();
     km_fill_kernel<<<(unsigned)nb, 32, smem, st>>>(assign, n, L, k, w.blk.as<int32_t>(), w.offsets.as<int64_t>(), w.members.as<int32_t>());
     B2_LAUNCH_CHECK();
-    dim3 grid((unsigned)k, (unsigned)ceil_div(d, 128));
-    km_accumulate_kernel<<<grid, 128, 0, st>>>(x, idx->dtype, d, row_ids, w.members.as<int32_t>(), w.offsets.as<int64_t>(), cent,
-                                               w.hassign.as<float>(), normalize);
+    const int V = idx->dtype == B2_BF16 ? 8 : 4;
+    const bool vec_ok = d % V == 0 && d / V <= 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    if (vec_ok) {
+        const int threads = (int)round_up(d / V, 32);
+        if (idx->dtype == B2_BF16)
+            km_accumulate_vec_kernel<true><<<(unsigned)k, threads, 0, st>>>(x, d, row_ids, w.members.as<int32_t>(), w.offsets.as<int64_t>(),
+                                                                           cent_old, cent_out, w.hassign.as<float>(), obj, normalize);
+        else
+            km_accumulate_vec_kernel<false><<<(unsigned)k, threads, 0, st>>>(x, d, row_ids, w.members.as<int32_t>(), w.offsets.as<int64_t>(),
+                                                                            cent_old, cent_out, w.hassign.as<float>(), obj, normalize);
+    } else {
+        dim3 grid((unsigned)k, (unsigned)ceil_div(d, 128));
+        km_accumulate_kernel<<<grid, 128, 0, st>>>(x, idx->dtype, d, row_ids, w.members.as<int32_t>(), w.offsets.as<int64_t>(), cent_old,
+                                                   cent_out, w.hassign.as<float>(), obj, normalize);
+    }
     B2_LAUNCH_CHECK();
     return B2_OK;
 }
 
-// B2_KM_TIMING=1: per-phase wall clock of b2_kmeans on stderr (each phase closed by a stream synchronise, so the phases
-// no longer overlap with the host work between them: a diagnostic, not a benchmark mode)
+// B2_KM_TIMING=1: per-phase wall clock of b2_kmeans on stderr (each phase closed by a stream synchronise: a diagnostic, not a
+// benchmark mode)
 struct KmTimer {
     bool on;
     cudaStream_t st;
     std::chrono::steady_clock::time_point t0;
-    double acc[6] = {0, 0, 0, 0, 0, 0};  // setup, assign, assign:filter, update, split/host, final
+    double acc[6] = {0, 0, 0, 0, 0, 0};  // setup, assign, assign:filter, update, -, final
+    int64_t second_level = 0;
     KmTimer(cudaStream_t s) : st(s) {
         const char* e = getenv("B2_KM_TIMING");
         on = e && atoi(e) != 0;
@@ -287,11 +570,36 @@ struct KmTimer {
     void report(int64_t m, int64_t nx, int k, int d, int niter) const {
         if (!on) return;
         fprintf(stderr,
-                "[b2 kmeans timing] m=%lld train=%lld k=%d d=%d niter=%d | setup %.2f ms | %d x assign %.2f ms (filter kernel %.2f) | "
-                "%d x update %.2f ms | obj/split host %.2f ms | final assign %.2f ms\n",
-                (long long)m, (long long)nx, k, d, niter, acc[0], niter, acc[1], acc[2], niter, acc[3], acc[4], acc[5]);
+                "[b2 kmeans timing] m=%lld train=%lld k=%d d=%d niter=%d | setup %.2f ms | %d x assign %.2f ms (filter kernel %.2f, "
+                "second-level points %lld) | %d x update+split %.2f ms | final assign %.2f ms\n",
+                (long long)m, (long long)nx, k, d, niter, acc[0], niter, acc[1], acc[2], (long long)second_level, niter, acc[3], acc[5]);
     }
 };
+
+// the point set of a call: all rows of the index, or the rows ids[0..m) gathered into w.pts; norms alongside
+int point_set(b2_index* idx, const int64_t* ids_dev, int64_t m, KmWork& w, const void*& P, const float*& Pn, cudaStream_t st) {
+    P = idx->store.p;
+    Pn = idx->view.norm2;
+    if (!ids_dev) return B2_OK;
+    const int d = idx->d;
+    B2_TRY(w.pts.ensure((size_t)std::max<int64_t>(m, 1) * d * esize(idx->dtype)));
+    B2_TRY(w.pts_norm2.ensure((size_t)std::max<int64_t>(m, 1) * sizeof(float)));
+    B2_TRY(w.scalar.ensure(64));
+    int* err = reinterpret_cast<int*>(w.scalar.as<char>() + 16);
+    B2_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
+    B2_TRY(launch_gather_rows(idx->store.p, idx->dtype, d, ids_dev, m, idx->n, w.pts.p, err, st));
+    B2_TRY(launch_row_norms(w.pts.p, idx->dtype, m, d, w.pts_norm2.as<float>(), w.scalar.as<float>() + 8, st));
+    int herr = 0;
+    B2_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    if (herr) {
+        set_error("ids contains a position outside [0, %lld)", (long long)idx->n);
+        return B2_ERANGE;
+    }
+    P = w.pts.p;
+    Pn = w.pts_norm2.as<float>();
+    return B2_OK;
+}
 
 int kmeans_impl(b2_index* idx, const int64_t* ids_host, int64_t m, int k, int niter, int64_t seed, int full_lloyd, int64_t* out_assign,
                 float* out_centroids, float* out_obj, KmWork& w) {
@@ -299,121 +607,100 @@ int kmeans_impl(b2_index* idx, const int64_t* ids_host, int64_t m, int k, int ni
     cudaStream_t st = idx->stream;
     KmTimer tm(st);
     const size_t es = esize(idx->dtype);
-    // the point set: rows ids[0..m) of the index (device id list), or all rows
     const int64_t* ids_dev = nullptr;
     if (ids_host) {
-        for (int64_t i = 0; i < m; ++i)
-            if (ids_host[i] < 0 || ids_host[i] >= idx->n) {
-                set_error("ids contains a position outside [0, %lld)", (long long)idx->n);
-                return B2_ERANGE;
-            }
         B2_TRY(w.ids.ensure((size_t)std::max<int64_t>(m, 1) * sizeof(int64_t)));
         B2_CUDA(cudaMemcpyAsync(w.ids.p, ids_host, (size_t)m * sizeof(int64_t), cudaMemcpyHostToDevice, st));
         ids_dev = w.ids.as<int64_t>();
     }
-    // materialise the point matrix P[m,d] (index dtype) when it is not simply the whole index
-    const void* P = idx->store.p;
-    DevBuf pts;
-    struct Guard { DevBuf& b; ~Guard() { b.release(); } } pts_guard{pts};
-    if (ids_dev) {
-        B2_TRY(pts.ensure((size_t)std::max<int64_t>(m, 1) * d * es));
-        B2_TRY(idx->scalar.ensure(64));
-        int* err = reinterpret_cast<int*>(idx->scalar.as<char>() + 16);
-        B2_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
-        B2_TRY(launch_gather_rows(idx->store.p, idx->dtype, d, ids_dev, m, idx->n, pts.p, err, st));
-        P = pts.p;
-    }
+    const void* P;
+    const float* Pn;
+    B2_TRY(point_set(idx, ids_dev, m, w, P, Pn, st));
     // training set (faiss ClusteringParameters: max_points_per_centroid = 256)
     int64_t nx = m;
     const void* T = P;
+    const float* Tn = Pn;
     const int64_t max_pts = (int64_t)k * 256;
+    std::vector<int64_t> perm;
     if (!full_lloyd && nx > max_pts) {
-        std::vector<int64_t> perm;
-        rand_perm(perm, nx, seed);
-        perm.resize(max_pts);
+        rand_perm_prefix(perm, nx, max_pts, seed);
         nx = max_pts;
-        DevBuf perm_dev;
-        int rc = perm_dev.ensure((size_t)nx * sizeof(int64_t));
-        if (rc == B2_OK) rc = w.train.ensure((size_t)nx * d * es);
-        if (rc == B2_OK) {
-            cudaMemcpyAsync(perm_dev.p, perm.data(), (size_t)nx * sizeof(int64_t), cudaMemcpyHostToDevice, st);
-            int* err = reinterpret_cast<int*>(idx->scalar.as<char>() + 16);
-            rc = launch_gather_rows(P, idx->dtype, d, perm_dev.as<int64_t>(), nx, m, w.train.p, err, st);
-            cudaStreamSynchronize(st);
-        }
-        perm_dev.release();
-        if (rc != B2_OK) return rc;
+        B2_TRY(w.perm.ensure((size_t)nx * sizeof(int64_t)));
+        B2_TRY(w.train.ensure((size_t)nx * d * es));
+        B2_TRY(w.train_norm2.ensure((size_t)nx * sizeof(float)));
+        B2_TRY(w.scalar.ensure(64));
+        B2_CUDA(cudaMemcpyAsync(w.perm.p, perm.data(), (size_t)nx * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        int* err = reinterpret_cast<int*>(w.scalar.as<char>() + 16);
+        B2_TRY(launch_gather_rows(P, idx->dtype, d, w.perm.as<int64_t>(), nx, m, w.train.p, err, st));
+        B2_TRY(launch_row_norms(w.train.p, idx->dtype, nx, d, w.train_norm2.as<float>(), w.scalar.as<float>() + 8, st));
+        B2_CUDA(cudaStreamSynchronize(st));  // `perm` (host vector) is reused below
         T = w.train.p;
+        Tn = w.train_norm2.as<float>();
     }
-    B2_TRY(w.cent.ensure((size_t)k * d * sizeof(float)));
-    float* cent = w.cent.as<float>();
-    std::vector<float> h_obj(std::max(niter, 1), 0.f);
+    B2_TRY(w.cent[0].ensure((size_t)k * d * sizeof(float)));
+    B2_TRY(w.cent[1].ensure((size_t)k * d * sizeof(float)));
+    int cur = 0;
     if (nx == k) {
         // "Number of training points same as number of centroids, just copying"
-        rows_to_f32_kernel<<<148, 256, 0, st>>>(T, idx->dtype, d, nullptr, k, cent);
+        rows_to_f32_kernel<<<148, 256, 0, st>>>(T, idx->dtype, d, nullptr, k, w.cent[0].as<float>());
         B2_LAUNCH_CHECK();
     } else {
-        std::vector<int64_t> perm;
-        rand_perm(perm, nx, seed + 1);
-        DevBuf perm_dev;
-        int rc = perm_dev.ensure((size_t)k * sizeof(int64_t));
-        if (rc != B2_OK) return rc;
-        cudaMemcpyAsync(perm_dev.p, perm.data(), (size_t)k * sizeof(int64_t), cudaMemcpyHostToDevice, st);
-        rows_to_f32_kernel<<<148, 256, 0, st>>>(T, idx->dtype, d, perm_dev.as<int64_t>(), k, cent);
-        g_stats[ST_LAUNCHES]++;
-        cudaStreamSynchronize(st);
-        perm_dev.release();
-        B2_TRY(w.dis.ensure((size_t)nx * sizeof(float)));
+        rand_perm_prefix(perm, nx, k, seed + 1);
+        B2_TRY(w.perm.ensure((size_t)k * sizeof(int64_t)));
+        B2_CUDA(cudaMemcpyAsync(w.perm.p, perm.data(), (size_t)k * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        rows_to_f32_kernel<<<148, 256, 0, st>>>(T, idx->dtype, d, w.perm.as<int64_t>(), k, w.cent[0].as<float>());
+        B2_LAUNCH_CHECK();
+        B2_CUDA(cudaStreamSynchronize(st));
         B2_TRY(w.assign.ensure((size_t)nx * sizeof(int64_t)));
-        B2_TRY(w.obj.ensure(64));
-        std::vector<float> hassign(k), hcent;
+        B2_TRY(w.obj.ensure((size_t)std::max(niter, 1) * sizeof(double)));
+        B2_CUDA(cudaMemsetAsync(w.obj.p, 0, (size_t)std::max(niter, 1) * sizeof(double), st));
         tm.lap(0);
         for (int it = 0; it < niter; ++it) {
-            B2_TRY(assign_points(idx, T, nx, cent, k, w, w.dis.as<float>(), w.assign.as<int64_t>(), st));
+            int64_t n2 = 0;
+            B2_TRY(assign_points(idx, T, Tn, nx, w.cent[cur].as<float>(), k, w, w.assign.as<int64_t>(), st, &n2));
             tm.lap(1);
+            tm.second_level += n2;
             if (tm.on && idx->last_filter_ms > 0) tm.acc[2] += idx->last_filter_ms;
-            B2_CUDA(cudaMemsetAsync(w.obj.p, 0, sizeof(double), st));
-            sum_f32_kernel<<<148, 256, 0, st>>>(w.dis.as<float>(), nx, w.obj.as<double>());
+            B2_TRY(update_centroids(idx, T, nullptr, nx, w.assign.as<int64_t>(), k, w, out_obj ? w.cent[cur].as<float>() : nullptr,
+                                    w.cent[cur ^ 1].as<float>(), w.obj.as<double>() + it, st, /*normalize=*/1));
+            km_split_kernel<<<1, 256, 0, st>>>(d, k, nx, w.hassign.as<float>(), w.cent[cur ^ 1].as<float>());
             B2_LAUNCH_CHECK();
-            B2_TRY(update_centroids(idx, T, nullptr, nx, w.assign.as<int64_t>(), k, w, cent, st));
+            cur ^= 1;
             tm.lap(3);
-            double obj = 0;
-            B2_CUDA(cudaMemcpyAsync(&obj, w.obj.p, sizeof(double), cudaMemcpyDeviceToHost, st));
-            B2_CUDA(cudaMemcpyAsync(hassign.data(), w.hassign.p, (size_t)k * sizeof(float), cudaMemcpyDeviceToHost, st));
-            B2_CUDA(cudaStreamSynchronize(st));
-            h_obj[it] = (float)obj;
-            bool any_empty = false;
-            for (int c = 0; c < k; ++c) any_empty |= hassign[c] == 0;
-            if (any_empty) {
-                hcent.resize((size_t)k * d);
-                B2_CUDA(cudaMemcpy(hcent.data(), cent, (size_t)k * d * sizeof(float), cudaMemcpyDeviceToHost));
-                split_clusters_host(d, k, nx, hassign, hcent);
-                B2_CUDA(cudaMemcpy(cent, hcent.data(), (size_t)k * d * sizeof(float), cudaMemcpyHostToDevice));
-            }
-            tm.lap(4);
         }
     }
     tm.lap(0);
     // lotus/utils.py:65 kmeans.index.search(vec_set, 1) over ALL m points
-    DevBuf fin_dis, fin_assign;
-    int rc = fin_dis.ensure((size_t)std::max<int64_t>(m, 1) * sizeof(float));
-    if (rc == B2_OK) rc = fin_assign.ensure((size_t)std::max<int64_t>(m, 1) * sizeof(int64_t));
-    if (rc == B2_OK) rc = assign_points(idx, P, m, cent, k, w, fin_dis.as<float>(), fin_assign.as<int64_t>(), st);
-    if (rc == B2_OK) {
-        cudaMemcpyAsync(out_assign, fin_assign.p, (size_t)m * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
-        if (out_centroids) cudaMemcpyAsync(out_centroids, cent, (size_t)k * d * sizeof(float), cudaMemcpyDeviceToHost, st);
-        if (cudaStreamSynchronize(st) != cudaSuccess) {
-            set_error("k-means failed on the device: %s", cudaGetErrorString(cudaGetLastError()));
-            rc = B2_ECUDA;
-        }
+    B2_TRY(w.fin_assign.ensure((size_t)std::max<int64_t>(m, 1) * sizeof(int64_t)));
+    B2_TRY(assign_points(idx, P, Pn, m, w.cent[cur].as<float>(), k, w, w.fin_assign.as<int64_t>(), st));
+    B2_CUDA(cudaMemcpyAsync(out_assign, w.fin_assign.p, (size_t)m * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (out_centroids) B2_CUDA(cudaMemcpyAsync(out_centroids, w.cent[cur].p, (size_t)k * d * sizeof(float), cudaMemcpyDeviceToHost, st));
+    std::vector<double> h_obj(std::max(niter, 1), 0.0);
+    if (out_obj && nx != k && niter > 0) B2_CUDA(cudaMemcpyAsync(h_obj.data(), w.obj.p, (size_t)niter * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (cudaStreamSynchronize(st) != cudaSuccess) {
+        set_error("k-means failed on the device: %s", cudaGetErrorString(cudaGetLastError()));
+        return B2_ECUDA;
     }
     tm.lap(5);
     tm.report(m, nx, k, d, niter);
-    fin_dis.release();
-    fin_assign.release();
-    if (rc == B2_OK && out_obj)
-        for (int it = 0; it < niter; ++it) out_obj[it] = h_obj[it];
-    return rc;
+    if (out_obj)
+        for (int it = 0; it < niter; ++it) out_obj[it] = (float)h_obj[it];
+    return B2_OK;
+}
+
+KmWork& work_of(b2_index* idx) {
+    if (!idx->km) idx->km = new KmWork();
+    return *idx->km;
+}
+
+int check_ids_host(b2_index* idx, const int64_t* ids, int64_t m) {
+    if (!ids) return B2_OK;
+    for (int64_t i = 0; i < m; ++i)
+        if (ids[i] < 0 || ids[i] >= idx->n) {
+            set_error("ids contains a position outside [0, %lld)", (long long)idx->n);
+            return B2_ERANGE;
+        }
+    return B2_OK;
 }
 
 }  // namespace
@@ -429,12 +716,50 @@ int b2_kmeans(b2_index* idx, const int64_t* ids, int64_t m, int32_t k, int32_t n
     if (!ids) m = idx->n;
     if (k <= 0 || niter < 0 || m < 0 || !out_assign) { set_error("bad k-means arguments (k=%d niter=%d m=%lld)", k, niter, (long long)m); return B2_EINVAL; }
     if (m < k) { set_error("Number of training points (%lld) should be at least as large as number of clusters (%d)", (long long)m, k); return B2_EINVAL; }
+    if (k > 0x7fffff00 / 2) { set_error("k=%d too large", k); return B2_ERANGE; }
+    B2_TRY(check_ids_host(idx, ids, m));
     DeviceGuard guard(idx->device);
-    KmWork w;
+    KmWork& w = work_of(idx);
     const int rc = kmeans_impl(idx, ids, m, k, niter, seed, full_lloyd, out_assign, out_centroids, out_obj, w);
     cudaStreamSynchronize(idx->stream);
-    w.release();
+    // the large per-call buffers go back; the small ones stay with the handle for the next call
+    DevBuf* big[] = {&w.pts, &w.pts_norm2, &w.train, &w.train_norm2, &w.assign, &w.members, &w.flag_ids, &w.sub, &w.fin_assign, &w.ids, &w.perm};
+    for (DevBuf* b : big) b->release();
     return rc;
+}
+
+int b2_kmeans_assign_dev(b2_index* idx, const int64_t* ids_dev, int64_t m, const float* centroids_dev, int32_t k, int64_t* assign_dev,
+                         float* dist_dev, void* stream) {
+    if (!idx) { set_error("Index not loaded"); return B2_EINVAL; }
+    if (!ids_dev) m = idx->n;
+    if (k <= 0 || m < 0 || !centroids_dev || (m > 0 && !assign_dev)) { set_error("bad arguments"); return B2_EINVAL; }
+    if (m == 0) return B2_OK;
+    DeviceGuard guard(idx->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    KmWork& w = work_of(idx);
+    const void* P;
+    const float* Pn;
+    B2_TRY(point_set(idx, ids_dev, m, w, P, Pn, st));
+    B2_TRY(assign_points(idx, P, Pn, m, centroids_dev, k, w, assign_dev, st));
+    if (dist_dev) B2_TRY(launch_exact_l2_assigned(P, idx->dtype, m, idx->d, centroids_dev, assign_dev, dist_dev, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    return B2_OK;
+}
+
+int b2_kmeans_accumulate_dev(b2_index* idx, const int64_t* ids_dev, int64_t m, const int64_t* assign_dev, int32_t k,
+                             const float* centroids_dev, float* sums_dev, float* counts_dev, double* obj_dev, void* stream) {
+    if (!idx) { set_error("Index not loaded"); return B2_EINVAL; }
+    if (!ids_dev) m = idx->n;
+    if (k <= 0 || m < 0 || (m > 0 && !assign_dev) || !sums_dev || !counts_dev) { set_error("bad arguments"); return B2_EINVAL; }
+    if (obj_dev && !centroids_dev) { set_error("the objective needs the centroids the assignment was made against"); return B2_EINVAL; }
+    DeviceGuard guard(idx->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    KmWork& w = work_of(idx);
+    B2_TRY(update_centroids(idx, idx->store.p, ids_dev, m, assign_dev, k, w, obj_dev ? centroids_dev : nullptr, sums_dev, obj_dev, st,
+                            /*normalize=*/0));
+    B2_CUDA(cudaMemcpyAsync(counts_dev, w.hassign.p, (size_t)k * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    return B2_OK;
 }
 
 int b2_kmeans_accumulate(b2_index* idx, const int64_t* ids, int64_t m, const int64_t* assign, int32_t k, float* out_sums,
@@ -442,16 +767,16 @@ int b2_kmeans_accumulate(b2_index* idx, const int64_t* ids, int64_t m, const int
     if (!idx) { set_error("Index not loaded"); return B2_EINVAL; }
     if (!ids) m = idx->n;
     if (k <= 0 || m < 0 || !assign || !out_sums || !out_counts) { set_error("bad arguments"); return B2_EINVAL; }
-    for (int64_t i = 0; i < m; ++i) {
+    for (int64_t i = 0; i < m; ++i)
         if (assign[i] < 0 || assign[i] >= k) { set_error("assign[%lld] = %lld outside [0, %d)", (long long)i, (long long)assign[i], k); return B2_ERANGE; }
-        if (ids && (ids[i] < 0 || ids[i] >= idx->n)) { set_error("ids contains a position outside [0, %lld)", (long long)idx->n); return B2_ERANGE; }
-    }
+    B2_TRY(check_ids_host(idx, ids, m));
     DeviceGuard guard(idx->device);
     cudaStream_t st = idx->stream;
-    KmWork w;
-    DevBuf d_assign;
-    int rc = w.cent.ensure((size_t)k * idx->d * sizeof(float));
-    if (rc == B2_OK) rc = d_assign.ensure((size_t)std::max<int64_t>(m, 1) * sizeof(int64_t));
+    KmWork& w = work_of(idx);
+    DevBuf d_assign, d_sums, d_counts;
+    int rc = d_assign.ensure((size_t)std::max<int64_t>(m, 1) * sizeof(int64_t));
+    if (rc == B2_OK) rc = d_sums.ensure((size_t)k * idx->d * sizeof(float));
+    if (rc == B2_OK) rc = d_counts.ensure((size_t)k * sizeof(float));
     const int64_t* ids_dev = nullptr;
     if (rc == B2_OK && ids) {
         rc = w.ids.ensure((size_t)std::max<int64_t>(m, 1) * sizeof(int64_t));
@@ -462,11 +787,11 @@ int b2_kmeans_accumulate(b2_index* idx, const int64_t* ids, int64_t m, const int
     }
     if (rc == B2_OK) {
         cudaMemcpyAsync(d_assign.p, assign, (size_t)m * sizeof(int64_t), cudaMemcpyHostToDevice, st);
-        rc = update_centroids(idx, idx->store.p, ids_dev, m, d_assign.as<int64_t>(), k, w, w.cent.as<float>(), st, /*normalize=*/0);
+        rc = b2_kmeans_accumulate_dev(idx, ids_dev, m, d_assign.as<int64_t>(), k, nullptr, d_sums.as<float>(), d_counts.as<float>(), nullptr, st);
     }
     if (rc == B2_OK) {
-        cudaMemcpyAsync(out_sums, w.cent.p, (size_t)k * idx->d * sizeof(float), cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(out_counts, w.hassign.p, (size_t)k * sizeof(float), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(out_sums, d_sums.p, (size_t)k * idx->d * sizeof(float), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(out_counts, d_counts.p, (size_t)k * sizeof(float), cudaMemcpyDeviceToHost, st);
         if (cudaStreamSynchronize(st) != cudaSuccess) {
             set_error("k-means accumulate failed on the device: %s", cudaGetErrorString(cudaGetLastError()));
             rc = B2_ECUDA;
@@ -474,8 +799,9 @@ int b2_kmeans_accumulate(b2_index* idx, const int64_t* ids, int64_t m, const int
     } else {
         cudaStreamSynchronize(st);
     }
-    w.release();
     d_assign.release();
+    d_sums.release();
+    d_counts.release();
     return rc;
 }
 
@@ -485,35 +811,27 @@ int b2_kmeans_assign(b2_index* idx, const int64_t* ids, int64_t m, const float* 
     if (!ids) m = idx->n;
     if (k <= 0 || m < 0 || !centroids || (m > 0 && !out_assign)) { set_error("bad arguments"); return B2_EINVAL; }
     if (m == 0) return B2_OK;
+    B2_TRY(check_ids_host(idx, ids, m));
     DeviceGuard guard(idx->device);
     cudaStream_t st = idx->stream;
     const int d = idx->d;
-    KmWork w;
-    DevBuf pts, dis, asg;
-    auto cleanup = [&]() { cudaStreamSynchronize(st); w.release(); pts.release(); dis.release(); asg.release(); };
-    int rc = w.cent.ensure((size_t)k * d * sizeof(float));
-    if (rc == B2_OK) rc = dis.ensure((size_t)m * sizeof(float));
+    KmWork& w = work_of(idx);
+    DevBuf cent, dis, asg;
+    auto cleanup = [&]() { cudaStreamSynchronize(st); cent.release(); dis.release(); asg.release(); w.pts.release(); w.pts_norm2.release(); };
+    int rc = cent.ensure((size_t)k * d * sizeof(float));
+    if (rc == B2_OK && out_dist) rc = dis.ensure((size_t)m * sizeof(float));
     if (rc == B2_OK) rc = asg.ensure((size_t)m * sizeof(int64_t));
-    const void* P = idx->store.p;
+    const int64_t* ids_dev = nullptr;
     if (rc == B2_OK && ids) {
         rc = w.ids.ensure((size_t)m * sizeof(int64_t));
-        if (rc == B2_OK) rc = pts.ensure((size_t)m * d * esize(idx->dtype));
-        if (rc == B2_OK) rc = idx->scalar.ensure(64);
         if (rc == B2_OK) {
-            int* err = reinterpret_cast<int*>(idx->scalar.as<char>() + 16);
-            cudaMemsetAsync(err, 0, sizeof(int), st);
             cudaMemcpyAsync(w.ids.p, ids, (size_t)m * sizeof(int64_t), cudaMemcpyHostToDevice, st);
-            rc = launch_gather_rows(idx->store.p, idx->dtype, d, w.ids.as<int64_t>(), m, idx->n, pts.p, err, st);
-            int herr = 0;
-            cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st);
-            cudaStreamSynchronize(st);
-            if (rc == B2_OK && herr) { set_error("ids contains a position outside [0, %lld)", (long long)idx->n); rc = B2_ERANGE; }
-            P = pts.p;
+            ids_dev = w.ids.as<int64_t>();
         }
     }
     if (rc == B2_OK) {
-        cudaMemcpyAsync(w.cent.p, centroids, (size_t)k * d * sizeof(float), cudaMemcpyHostToDevice, st);
-        rc = assign_points(idx, P, m, w.cent.as<float>(), k, w, dis.as<float>(), asg.as<int64_t>(), st);
+        cudaMemcpyAsync(cent.p, centroids, (size_t)k * d * sizeof(float), cudaMemcpyHostToDevice, st);
+        rc = b2_kmeans_assign_dev(idx, ids_dev, m, cent.as<float>(), k, asg.as<int64_t>(), out_dist ? dis.as<float>() : nullptr, st);
     }
     if (rc == B2_OK) {
         cudaMemcpyAsync(out_assign, asg.p, (size_t)m * sizeof(int64_t), cudaMemcpyDeviceToHost, st);

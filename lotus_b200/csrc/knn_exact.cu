@@ -212,20 +212,6 @@ __global__ void convert_pad_kernel(const void* x, int dtype, int64_t n, int d, v
     }
 }
 
-// out[r, c] = bf16(x[r,c]) and out[r, dp + c] = bf16(x[r,c] - bf16(x[r,c])) for c < d, zero padding up to dp (see MatView)
-__global__ void split_bf16_kernel(const void* x, int dtype, int64_t n, int d, __nv_bfloat16* out, int64_t dp) {
-    const int64_t total = n * dp;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = t / dp;
-        const int c = (int)(t - r * dp);
-        const float v = c < d ? elem_f32(x, dtype, (size_t)(r * d + c)) : 0.f;
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-        out[r * 2 * dp + c] = hi;
-        out[r * 2 * dp + dp + c] = lo;
-    }
-}
-
 // out[i,:] = x[ids[i],:] — one warp per row, 16-byte copies when the row size allows
 __global__ void gather_rows_kernel(const char* x, size_t row_bytes, const int64_t* ids, int64_t m, int64_t n, char* out,
                                    int* err_flag) {
@@ -310,11 +296,14 @@ struct FinalizeParams {
     float* out_scores;
     int64_t* out_idx;
     int32_t* flags;
+    int32_t* sel;        // [nq] queries whose certificate failed, in arbitrary order (nullable)
+    int32_t* sel_count;  // number of entries in sel (device counter, zeroed by the caller)
     int64_t nq;
     int64_t id_offset;
     int32_t d, dtype, q_dtype, metric, k, kp, n_splits;  // n_splits = number of candidate lists per query, kp = survivors kept
     int32_t list_len;                                    // entries per candidate list (<= 32*R)
     float rel_eps, max_norm;
+    const float* max_norm_dev;  // nullable: overrides max_norm
 };
 
 constexpr int FIN_WARPS = 4;
@@ -334,6 +323,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(const Finalize
 
     const int64_t q = blockIdx.x * (int64_t)FIN_WARPS + warp;
     if (q >= p.nq) return;
+    const float max_norm = p.max_norm_dev ? __ldg(p.max_norm_dev) : p.max_norm;
     const bool is_l2 = p.metric == B2_METRIC_L2;
     const bool vec = (p.d % 4) == 0;
     const size_t esz = p.dtype == B2_F32 ? 4 : 2;
@@ -387,7 +377,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(const Finalize
         for (int off = 16; off >= 1; off >>= 1) bound = fmaxf(bound, __shfl_xor_sync(FULL, bound, off));
     }
     // margin between a filter score and the exact score it stands for (same quantity the certificate uses below)
-    const double qn_m = sqrt(qn2), mx_m = (double)p.max_norm;
+    const double qn_m = sqrt(qn2), mx_m = (double)max_norm;
     const double eps_f = is_l2 ? 2.0 * (double)p.rel_eps * qn_m * mx_m + 2.4e-7 * (mx_m * mx_m + 2.0 * qn_m * mx_m) + 1e-30
                                : (double)p.rel_eps * qn_m * mx_m + 1e-30;
     // Pruning before the (expensive) re-score: the k best survivors BY FILTER SCORE have exact scores >= t_k - eps, so a
@@ -525,10 +515,10 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(const Finalize
             const double qn = sqrt(qn2);
             const double v = (double)best_first_unkey((uint32_t)(s_keys[k - 1] >> 32), p.metric);
             if (!is_l2) {
-                const double eps = (double)p.rel_eps * qn * (double)p.max_norm + 1e-30;
+                const double eps = (double)p.rel_eps * qn * (double)max_norm + 1e-30;
                 certified = ((double)bound + eps) < v;
             } else {
-                const double mx = (double)p.max_norm;
+                const double mx = (double)max_norm;
                 const double eps_s = 2.0 * (double)p.rel_eps * qn * mx + 2.4e-7 * (mx * mx + 2.0 * qn * mx) + 1e-30;
                 // discarded rows have exact L2 >= qn2 - (bound + eps_s); allow for the fp32 rounding of v
                 certified = (qn2 - (double)bound - eps_s) > v * (1.0 + 2.4e-7) + 1e-30;
@@ -552,7 +542,10 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(const Finalize
         p.out_scores[(size_t)q * k + o] = sc;
         p.out_idx[(size_t)q * k + o] = oid;
     }
-    if (lane == 0) p.flags[q] = certified ? 0 : 1;
+    if (lane == 0) {
+        p.flags[q] = certified ? 0 : 1;
+        if (!certified && p.sel) p.sel[atomicAdd(p.sel_count, 1)] = (int32_t)q;
+    }
 }
 
 // ---- dense exact path -----------------------------------------------------------------------------------------
@@ -844,6 +837,30 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const float* scores, co
     }
 }
 
+// out[i] = canonical ||pts[i] - cent[assign[i]]||^2 (what kmeans.index.search(x, 1) reports for the winner). Warp per point.
+__global__ void exact_l2_assigned_kernel(const void* pts, int dtype, int64_t m, int d, const float* cent, const int64_t* assign,
+                                         float* out) {
+    extern __shared__ __align__(16) float el_q[];  // [warps per block][d4]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int d4 = ((d + 3) >> 2) << 2;
+    float* q_s = el_q + (size_t)wib * d4;
+    const bool vec = (d % 4) == 0;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < m; i += nwarps) {
+        __syncwarp();
+        for (int t = lane; t < d4; t += 32) q_s[t] = t < d ? elem_f32(pts, dtype, (size_t)i * d + t) : 0.f;
+        __syncwarp();
+        const int64_t c = assign[i];
+        float r = FLT_MAX;
+        if (c >= 0) {
+            const double part = canonical_partial<true>(q_s, cent + (size_t)c * d, B2_F32, d, vec, lane);
+            r = (float)butterfly_sum(part);
+        }
+        if (lane == 0) out[i] = r;
+    }
+}
+
 int grid_for(int64_t work_items, int threads, int cap = 148 * 16) {
     int64_t g = ceil_div(work_items, threads);
     if (g < 1) g = 1;
@@ -871,9 +888,17 @@ int launch_row_norms(const void* x, int dtype, int64_t n, int d, float* norm2, f
     return B2_OK;
 }
 
-int launch_split_bf16(const void* x, int dtype, int64_t n, int d, void* out, int64_t split_dp, cudaStream_t stream) {
-    if (n <= 0) return B2_OK;
-    split_bf16_kernel<<<grid_for(n * split_dp, 256), 256, 0, stream>>>(x, dtype, n, d, reinterpret_cast<__nv_bfloat16*>(out), split_dp);
+int launch_exact_l2_assigned(const void* pts, int dtype, int64_t m, int d, const float* cent, const int64_t* assign, float* out,
+                             cudaStream_t stream) {
+    if (m <= 0) return B2_OK;
+    const int d4 = ((d + 3) >> 2) << 2;
+    const size_t smem = (size_t)8 * d4 * 4;
+    if (smem > 200 * 1024) {
+        set_error("embedding dimension %d too large for the exact distance kernel", d);
+        return B2_ERANGE;
+    }
+    if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(exact_l2_assigned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    exact_l2_assigned_kernel<<<grid_for(m * 32, 256, 148 * 8), 256, smem, stream>>>(pts, dtype, m, d, cent, assign, out);
     B2_LAUNCH_CHECK();
     return B2_OK;
 }
@@ -916,9 +941,11 @@ static int launch_finalize_r(const FinalizeParams& p, cudaStream_t stream) {
 int launch_finalize(const MatView& X, const void* q, int q_dtype, int64_t nq, int metric, int k, int kp, int list_len,
                     int n_splits, const float* cand_score, const int32_t* cand_id, const float* cand_thr,
                     float rel_eps, const int64_t* id_map, int64_t id_offset, float* out_scores, int64_t* out_idx,
-                    int32_t* flags, cudaStream_t stream) {
+                    int32_t* flags, int32_t* sel, int32_t* sel_count, cudaStream_t stream) {
     if (nq <= 0) return B2_OK;
     FinalizeParams p;
+    p.sel = sel;
+    p.sel_count = sel_count;
     p.store = X.store;
     p.q = q;
     p.cand_score = cand_score;
@@ -940,6 +967,7 @@ int launch_finalize(const MatView& X, const void* q, int q_dtype, int64_t nq, in
     p.n_splits = n_splits;
     p.rel_eps = rel_eps;
     p.max_norm = X.max_norm;
+    p.max_norm_dev = X.max_norm_dev;
     g_stats[ST_RESCORED] += nq * (int64_t)kp;
     if (kp <= 32) return launch_finalize_r<1>(p, stream);
     if (kp <= 64) return launch_finalize_r<2>(p, stream);

@@ -277,12 +277,11 @@ struct FilterParams {
     float* cand_thr;     // [nq, n_splits]
     int32_t nq;
     int32_t n;
-    int32_t num_kb;        // K-blocks per tile = ceil(d / elements per 128 B); 3x that in hi/lo split mode
-    int32_t split_kb;      // 0, or K-blocks per segment of the bf16 hi|lo split: segment 0 = q_hi.x_hi, 1 = q_hi.x_lo, 2 = q_lo.x_hi
+    int32_t num_kb;        // K-blocks per tile = ceil(d / elements per 128 B)
     int32_t n_mtiles;      // ceil(nq / 128)
     int32_t n_munits;      // schedulable query units: n_mtiles, or ceil(n_mtiles / 2) CTA pairs in cta_group::2 mode
     int32_t n_splits;
-    int32_t top1;             // host-side switch only: k == 1 and B2_FILTER_TOP1=1 -> the TOP1 kernel variant is launched
+    int32_t top1;             // host-side switch only: the TOP1 kernel variant is launched (k-means assignment)
     int32_t tiles_per_split;  // corpus tiles (of 256 rows) per split
     int32_t n_ntiles;         // ceil(n / 256)
     // all-pairs (dedup) schedule: the query matrix IS the corpus; an item is one query tile sweeping only the corpus tiles
@@ -372,12 +371,7 @@ __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap_q, const C
                 mbar_wait(&r.empty_bar[stage], phase ^ 1);
                 uint8_t* sa = r.stage_base + stage * SB;
                 uint8_t* sb = sa + STAGE_A_BYTES;
-                int ka = kb, kx = kb;  // K-block (operand column block) of the query / corpus operand
-                if (p.split_kb) {
-                    const int seg = kb / p.split_kb, rem = kb - seg * p.split_kb;
-                    ka = rem + (seg == 2 ? p.split_kb : 0);  // q_hi, q_hi, q_lo
-                    kx = rem + (seg == 1 ? p.split_kb : 0);  // x_hi, x_lo, x_hi
-                }
+                const int ka = kb, kx = kb;  // K-block (operand column block) of the query / corpus operand
                 if constexpr (TWO) {
                     // the leader's full barrier counts the bytes of BOTH CTAs (2 x 32 KB); only the leader arms it
                     if (sc.rank == 0) mbar_arrive_expect_tx(&r.full_bar[stage], 2 * SB);
@@ -1061,7 +1055,7 @@ bool filter_use_pair(int64_t nq) {
 
 // Number of corpus splits: enough work items to fill the machine, and few idle workers in the last wave.
 // In pair mode a worker is a CTA pair and a query unit is two query tiles.
-int filter_choose_splits(int64_t nq, int64_t n, int num_sms, bool two_cta) {
+int filter_choose_splits(int64_t nq, int64_t n, int num_sms, bool two_cta, bool top1) {
     {
         static int forced = -1;  // B2_FILTER_SPLITS: experiments only
         if (forced < 0) {
@@ -1081,7 +1075,7 @@ int filter_choose_splits(int64_t nq, int64_t n, int num_sms, bool two_cta) {
     const int64_t n_ntiles = ceil_div(n, BLOCK_N);
     // cost model (measured, profiles/README.md): an item costs its corpus tiles plus ~13 tile-times of list warm-up, the
     // kernel takes `waves` such items back to back, and every extra split adds two candidate lists per query to finalize
-    constexpr double kWarmupTiles = 13.0;
+    const double kWarmupTiles = top1 ? 1.0 : 13.0;  // the register-resident top-2 epilogue has no list to warm up
     int best = 1;
     double best_cost = 1e300;
     for (int s = 1; s <= 256 && s <= n_ntiles; ++s) {
@@ -1109,12 +1103,7 @@ int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int
     const bool tf32 = X.filt_dtype == B2_F32;
     const int kb_elems = tf32 ? 32 : 64;
     CUtensorMap tq, tx;
-    const bool split = X.split_dp > 0;  // bf16 hi|lo operands: both matrices are [rows, 2*split_dp] bf16
-    if (split && (tf32 || q_pitch != 2 * (int64_t)X.split_dp || X.filt_pitch != 2 * (int64_t)X.split_dp || X.split_dp % kb_elems)) {
-        set_error("internal: inconsistent hi/lo split view");
-        return B2_EINVAL;
-    }
-    const int64_t op_cols = split ? 2 * (int64_t)X.split_dp : X.d;
+    const int64_t op_cols = X.d;
     B2_TRY(make_tmap(&tq, q_filt, tf32, nq, op_cols, q_pitch, BLOCK_M));
     // pair mode: each CTA of the pair loads HALF of the 256-row corpus tile
     B2_TRY(make_tmap(&tx, X.filt, tf32, X.n, op_cols, X.filt_pitch, two_cta ? BLOCK_N / 2 : BLOCK_N));
@@ -1125,15 +1114,13 @@ int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int
     p.cand_thr = cand_thr;
     p.nq = (int32_t)nq;
     p.n = (int32_t)X.n;
-    p.split_kb = split ? (int32_t)(X.split_dp / kb_elems) : 0;
-    p.num_kb = split ? 3 * p.split_kb : (int32_t)ceil_div(X.d, kb_elems);
+    p.num_kb = (int32_t)ceil_div(X.d, kb_elems);
     p.n_mtiles = (int32_t)ceil_div(nq, BLOCK_M);
     p.n_munits = two_cta ? (p.n_mtiles + 1) / 2 : p.n_mtiles;
     p.n_ntiles = (int32_t)ceil_div(X.n, BLOCK_N);
     p.tiles_per_split = (int32_t)ceil_div(p.n_ntiles, n_splits);
     p.n_splits = n_splits;
-    static const bool top1_on = [] { const char* e = getenv("B2_FILTER_TOP1"); return e && atoi(e) != 0; }();
-    p.top1 = (top1 && top1_on && kp == 16) ? 1 : 0;
+    p.top1 = (top1 && kp == 16) ? 1 : 0;  // register-resident top-2 epilogue: requested by the k-means assignment path only
     p.pair_mode = 0;
     p.part = 0;
     p.nparts = 1;
@@ -1215,7 +1202,7 @@ int launch_pair_filter(const MatView& X, float thr, int part, int nparts, int32_
     p.nq = (int32_t)X.n;
     p.n = (int32_t)X.n;
     p.num_kb = (int32_t)ceil_div(X.d, kb_elems);
-    static const bool two = [] { const char* e = getenv("B2_PAIR_2CTA"); return e && atoi(e) != 0; }();
+    static const bool two = [] { const char* e = getenv("B2_PAIR_2CTA"); return e ? atoi(e) != 0 : true; }();  // default: CTA pairs
     const bool two_cta = two && ceil_div(X.n, BLOCK_M) >= 2;
     if (two_cta) B2_TRY(make_tmap(&tx, X.filt, tf32, X.n, X.d, X.filt_pitch, BLOCK_N / 2));  // each CTA stages half a corpus tile
     p.n_mtiles = (int32_t)ceil_div(X.n, BLOCK_M);

@@ -158,54 +158,61 @@ def sharded_threshold_pairs(index: "nv.Index", threshold: float, group=None):
     return ai[order], aj[order]
 
 
-def sharded_kmeans(index: "nv.Index", n_total: int, row_offset: int, k: int, niter: int = 20, seed: int = 1234, group=None):
+def sharded_kmeans(index: "nv.Index", n_total: int, row_offset: int, k: int, niter: int = 20, seed: int = 1234, group=None,
+                   want_obj: bool = True):
     """Full-Lloyd k-means over points row-sharded across ranks (`index` holds this rank's rows [row_offset, row_offset+n_local)).
     faiss's control flow (lotus/utils.py:61-65 -> faiss/Clustering.cpp): initial centroids = the first k points of
-    rand_perm(n_total, seed+1) (fetched from whichever rank owns them), then per iteration: exact assignment of the local
-    points (b2_kmeans_assign), per-shard point-order fp32 sums (b2_kmeans_accumulate), ONE all-reduce(sum) of the [k,d]
-    sums and [k] counts, division, split_clusters replayed identically on every rank. The cross-rank fp32 reduction
-    makes centroids agree with the single-process restatement to rounding, not bit-for-bit.
-    Returns (local assignment [n_local] int64, centroids [k,d] float32, objective per iteration)."""
+    rand_perm(n_total, seed+1) (fetched from whichever rank owns them), then per iteration, all on the device:
+    exact assignment of the local points (b2_kmeans_assign_dev), per-shard point-order fp32 sums + counts (+ the fp64
+    objective) in one pass (b2_kmeans_accumulate_dev), ONE NCCL all-reduce(sum) of the packed [k,d] sums | [k] counts,
+    division; split_clusters is replayed identically on every rank in the (rare) iterations that leave a cluster empty.
+    The cross-rank fp32 reduction makes centroids agree with the single-process restatement to rounding, not bit-for-bit
+    (DESIGN.md §6). Returns (local assignment [n_local] int64, centroids [k,d] float32, objective per iteration) as numpy."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    dev = torch.device("cuda", index.device) if (world > 1 and dist.get_backend(group) == "nccl") else torch.device("cpu")
+    dev = torch.device("cuda", index.device)
     n_local, d = index.n, index.d
-    # initial centroids: rows perm[:k] of the global matrix
-    rng = np.random.RandomState((seed + 1) & 0xFFFFFFFF)
-    raw = rng._bit_generator.random_raw(max(n_total, 1))  # std::mt19937 stream == faiss RandomGenerator
-    perm = np.arange(n_total, dtype=np.int64)
-    for i in range(min(k, n_total - 1)):  # only the first k entries of the Fisher-Yates shuffle are needed
-        i2 = i + int(raw[i]) % (n_total - i)
-        perm[i], perm[i2] = perm[i2], perm[i]
-    want = perm[:k]
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    # initial centroids: rows perm[:k] of the global matrix (only the first k steps of the Fisher-Yates shuffle are needed)
+    raw = np.random.RandomState((seed + 1) & 0xFFFFFFFF)._bit_generator.random_raw(max(min(k, n_total), 1))  # std::mt19937 stream
+    moved: dict[int, int] = {}
+    want = np.empty(k, dtype=np.int64)
+    for i in range(k):
+        if i + 1 < n_total:
+            i2 = i + int(raw[i]) % (n_total - i)
+            a, b = moved.get(i, i), moved.get(i2, i2)
+            moved[i], moved[i2] = b, a
+        want[i] = moved.get(i, i)
     mine = (want >= row_offset) & (want < row_offset + n_local)
-    cent = np.zeros((k, d), dtype=np.float32)
+    cent_h = np.zeros((k, d), dtype=np.float32)
     if mine.any():
         rows = index.gather(want[mine] - row_offset)
-        cent[mine] = nv.bf16_bits_to_f32(rows) if index.dtype == nv.BF16 else rows
+        cent_h[mine] = nv.bf16_bits_to_f32(rows) if index.dtype == nv.BF16 else rows
+    cent = torch.from_numpy(cent_h).to(dev)
     if world > 1:
-        t = torch.from_numpy(cent).to(dev)
-        dist.all_reduce(t, group=group)  # each row is non-zero on exactly one rank
-        cent = t.cpu().numpy()
-    objs = []
-    for _ in range(niter):
-        assign, dist2 = index.kmeans_assign(cent)
-        sums, counts = index.kmeans_accumulate(assign, k)
-        obj = np.array([float(dist2.astype(np.float64).sum())])
+        dist.all_reduce(cent, group=group)  # each row is non-zero on exactly one rank
+    packed = torch.empty(k * d + k, dtype=torch.float32, device=dev)
+    sums, counts = packed[:k * d].view(k, d), packed[k * d:]
+    assign = torch.empty(max(n_local, 1), dtype=torch.int64, device=dev)
+    obj = torch.zeros(max(niter, 1), dtype=torch.float64, device=dev)
+    for it in range(niter):
+        index.kmeans_assign_dev(cent.data_ptr(), k, assign.data_ptr(), stream=stream)
+        index.kmeans_accumulate_dev(assign.data_ptr(), k, sums.data_ptr(), counts.data_ptr(),
+                                    centroids_ptr=cent.data_ptr() if want_obj else 0,
+                                    obj_ptr=obj[it:].data_ptr() if want_obj else 0, stream=stream)
         if world > 1:
-            ts, tc, to = torch.from_numpy(sums).to(dev), torch.from_numpy(counts).to(dev), torch.from_numpy(obj).to(dev)
-            dist.all_reduce(ts, group=group)
-            dist.all_reduce(tc, group=group)
-            dist.all_reduce(to, group=group)
-            sums, counts, obj = ts.cpu().numpy(), tc.cpu().numpy(), to.cpu().numpy()
-        objs.append(float(obj[0]))
+            dist.all_reduce(packed, group=group)
         nz = counts > 0
-        cent = np.where(nz[:, None], sums * (np.float32(1) / np.where(nz, counts, 1)).astype(np.float32)[:, None], 0).astype(np.float32)
-        if not nz.all():
-            cent, counts = split_clusters_host(cent, counts, n_total)
-    assign, _ = index.kmeans_assign(cent)
-    return assign, cent, np.asarray(objs, dtype=np.float32)
+        inv = torch.reciprocal(torch.where(nz, counts, torch.ones_like(counts)))  # fp32 1/count, then one fp32 multiply: faiss's order
+        cent = torch.where(nz[:, None], sums * inv[:, None], torch.zeros_like(sums)).contiguous()
+        if not bool(nz.all()):
+            c_h, _ = split_clusters_host(cent.cpu().numpy(), counts.cpu().numpy(), n_total)
+            cent = torch.from_numpy(c_h).to(dev)
+    if world > 1 and want_obj and niter > 0:
+        dist.all_reduce(obj, group=group)
+    index.kmeans_assign_dev(cent.data_ptr(), k, assign.data_ptr(), stream=stream)  # same stream as the torch ops: ordered
+    return assign[:n_local].cpu().numpy(), cent.cpu().numpy(), obj[:niter].to(torch.float32).cpu().numpy()
 
 
 def split_clusters_host(centroids: np.ndarray, hassign: np.ndarray, n: int):
