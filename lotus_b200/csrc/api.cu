@@ -95,12 +95,12 @@ int search_core(b2_index* idx, const MatView& X, int metric, const void* q_dev, 
         return B2_OK;
     }
     const int kp = filter_kp_for_k(k);
-    const bool use_filter = kp != 0 && X.n >= 512;
-    int64_t npow2 = 1;
-    while (npow2 < X.n) npow2 <<= 1;
-    const bool full_sort = k > dense_select_max_k();  // dense path sorts whole rows: 12 bytes of workspace per padded column
-    const int64_t dense_rows_cap =
-        std::max<int64_t>(1, (int64_t)(256ull << 20) / (full_sort ? npow2 * 12 : X.n * 4));
+    const int min_splits = filter_min_splits_for_k(k);
+    // the filter needs a corpus worth tiling: two tiles at least, and for k > 64 enough tiles to cut into min_splits splits
+    // with k well below the rows of a split
+    const bool use_filter = kp != 0 && X.n >= 512 && ceil_div(X.n, 256) >= min_splits && X.n >= 4 * (int64_t)k;
+    const bool full_sort = k > dense_select_max_k();  // dense path sorts whole rows: score + two key buffers per column
+    const int64_t dense_rows_cap = std::max<int64_t>(1, (int64_t)(512ull << 20) / (std::max<int64_t>(X.n, 1) * (full_sort ? 24 : 4)));
     if (!use_filter) {
         if (k > dense_max_k()) {
             set_error("k=%d is not supported (max %d)", k, dense_max_k());
@@ -108,7 +108,7 @@ int search_core(b2_index* idx, const MatView& X, int metric, const void* q_dev, 
         }
         const int64_t rows = std::min<int64_t>(dense_rows_cap, nq);
         B2_TRY(idx->dense.ensure((size_t)rows * X.n * sizeof(float)));
-        if (full_sort) B2_TRY(idx->sort_keys.ensure((size_t)rows * npow2 * sizeof(uint64_t)));
+        if (full_sort) B2_TRY(idx->sort_keys.ensure(dense_sort_ws_bytes(rows, X.n)));
         B2_TRY(launch_dense_topk(X, q_dev, q_dtype, nq, nullptr, nq, metric, k, id_map, id_offset, idx->dense.as<float>(), rows,
                                  full_sort ? idx->sort_keys.as<uint64_t>() : nullptr, out_sc, out_id, st));
         g_stats[ST_FALLBACK] += nq;
@@ -122,14 +122,19 @@ int search_core(b2_index* idx, const MatView& X, int metric, const void* q_dev, 
     // queries that already have the filter's element type and a TMA-compatible pitch are streamed in place
     const bool q_in_place = q_dtype == filt_dtype && q_pitch == X.d && (reinterpret_cast<uintptr_t>(q_dev) & 15) == 0;
     // bound the candidate workspace: process the queries in chunks
-    const int64_t chunk = 1 << 20;
+    // bound the candidate workspace (nqc x n_splits x kp x 8 bytes) to a few GB: fewer queries per chunk when k needs many splits
+    const int64_t chunk = std::max<int64_t>(4096, std::min<int64_t>(1 << 20, (4LL << 30) / ((int64_t)std::max(min_splits, 8) * kp * 8)));
     for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
         const int64_t nqc = std::min<int64_t>(chunk, nq - q0);
         const char* qc = reinterpret_cast<const char*>(q_dev) + (size_t)q0 * X.d * esize(q_dtype);
         float* osc = out_sc + (size_t)q0 * k;
         int64_t* oid = out_id + (size_t)q0 * k;
         const bool two_cta = filter_use_pair(nqc);
-        const int n_splits = filter_choose_splits(nqc, X.n, dev_sms, two_cta);
+        const int n_splits = filter_choose_splits(nqc, X.n, dev_sms, two_cta, false, min_splits);
+        if (n_splits <= 0) {
+            set_error("internal: no valid corpus split for k=%d over %lld rows", k, (long long)X.n);
+            return B2_EINVAL;
+        }
         if (!q_in_place) B2_TRY(idx->q_filt.ensure((size_t)nqc * q_pitch * esize(filt_dtype)));
         const void* q_filt = q_in_place ? static_cast<const void*>(qc) : idx->q_filt.p;
         B2_TRY(idx->cand_score.ensure((size_t)nqc * n_splits * kp * sizeof(float)));

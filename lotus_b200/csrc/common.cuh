@@ -104,7 +104,8 @@ int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int
                       int n_splits, bool two_cta, float* cand_score, int32_t* cand_id, float* cand_thr, int device,
                       cudaStream_t stream, bool top1 = false);
 bool filter_use_pair(int64_t nq);
-int filter_choose_splits(int64_t nq, int64_t n, int num_sms, bool two_cta, bool top1 = false);
+int filter_choose_splits(int64_t nq, int64_t n, int num_sms, bool two_cta, bool top1 = false, int min_splits = 1);  // 0: impossible
+int filter_min_splits_for_k(int k);
 int launch_pair_filter(const MatView& X, float thr, int part, int nparts, int32_t* pair_i, int32_t* pair_j,
                        unsigned long long* pair_count, unsigned long long cap, int device, cudaStream_t stream);
 
@@ -128,6 +129,7 @@ int launch_dense_topk(const MatView& X, const void* q, int q_dtype, int64_t nq, 
                       int64_t dense_ws_rows, uint64_t* sort_ws, float* out_scores, int64_t* out_idx, cudaStream_t stream);
 int launch_merge_topk(const float* scores, const int64_t* idx, int g, int64_t nq, int k, int metric,
                       float* out_scores, int64_t* out_idx, cudaStream_t stream);
+size_t dense_sort_ws_bytes(int64_t rows, int64_t n);  // workspace of the full-sort path for `rows` score rows
 int dense_max_k();         // largest k any path supports
 int dense_select_max_k();  // largest k of the radix-select path (beyond it: full row sort)
 

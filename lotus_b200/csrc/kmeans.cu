@@ -25,17 +25,18 @@
 #include <unordered_map>
 #include <vector>
 
+#include "canonical.cuh"
 #include "index.cuh"
 
 namespace b2 {
 
 struct KmWork {
     DevBuf cent[2], cent_filt, cent_norm2, scalar, pts, pts_norm2, train, train_norm2, assign, members, offsets, totals, blk, hassign, ids,
-        obj, flag_ids, flag_count, sub, sub_dis, sub_assign, fin_assign, fin_dis, perm;
+        obj, flag_ids, flag_count, hard_ids, sub, sub_dis, sub_assign, fin_assign, fin_dis, perm;
     HostBuf h_count;
     void release() {
         DevBuf* all[] = {&cent[0], &cent[1], &cent_filt, &cent_norm2, &scalar, &pts, &pts_norm2, &train, &train_norm2, &assign, &members,
-                         &offsets, &totals, &blk, &hassign, &ids, &obj, &flag_ids, &flag_count, &sub, &sub_dis, &sub_assign, &fin_assign,
+                         &offsets, &totals, &blk, &hassign, &ids, &obj, &flag_ids, &flag_count, &hard_ids, &sub, &sub_dis, &sub_assign, &fin_assign,
                          &fin_dis, &perm};
         for (DevBuf* b : all) b->release();
         h_count.release();
@@ -49,8 +50,6 @@ void km_work_free(KmWork* w) {
 }
 
 namespace {
-
-constexpr unsigned FULL = 0xffffffffu;
 
 // First `take` entries of faiss/utils/random.cpp rand_perm(n, seed): Fisher-Yates with rng.rand_int(n - i) = mt() % (n - i).
 // Entry i is final after step i, so only `take` steps are replayed, over a sparse view of the (otherwise identity) array.
@@ -90,7 +89,7 @@ __global__ void rows_to_f32_kernel(const void* x, int dtype, int d, const int64_
 // third-best score in cand_thr (-inf when the list saw fewer than three centroids). score = 2 x.c - ||c||^2 (larger = nearer).
 __global__ void km_assign_finalize_kernel(const float* cand_score, const int32_t* cand_id, const float* cand_thr, int64_t m, int n_lists,
                                           int list_len, const float* pnorm2, const float* max_norm_dev, float rel_eps, int64_t* assign,
-                                          int64_t* flag_ids, int32_t* flag_count, int64_t base) {
+                                          int32_t* flag_local, int32_t* flag_count, int64_t base) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= m) return;
     float f1 = -INFINITY, f2 = -INFINITY;
@@ -120,7 +119,84 @@ __global__ void km_assign_finalize_kernel(const float* cand_score, const int32_t
     const double slack = 2.4e-7 * (qn2 + fmax(fabs((double)f1), fabs((double)f2)));
     const bool certain = c1 >= 0 && ((double)f1 - (double)f2) > 2.0 * eps_s + slack;  // false for NaN scores as well
     assign[base + i] = c1;
-    if (!certain) flag_ids[atomicAdd(flag_count, 1)] = base + i;
+    if (!certain) flag_local[atomicAdd(flag_count, 1)] = (int32_t)i;
+}
+
+// ---- step 4a: points the gap test left open, decided among their KNOWN contenders -------------------------------------------
+// Warp per flagged point. Every centroid whose exact score could reach the winner's is either one of the (at most two per list)
+// recorded candidates with a filter score within 2 eps of the best — those are re-scored with the canonical distance, ties to
+// the lowest id — or lies under a list's third-best bound; the same certificate as finalize_kernel then shows the bound cannot
+// reach the exact winner. Points that fail it go on to the general pipeline (hard_ids).
+__global__ void km_rescore_known_kernel(const void* pts, int dtype, int d, const float* cent, const float* cand_score, const int32_t* cand_id,
+                                        const float* cand_thr, int n_lists, int list_len, const float* pnorm2, const float* max_norm_dev,
+                                        float rel_eps, const int32_t* flag_local, const int32_t* flag_count, int64_t base, int64_t* assign,
+                                        int64_t* hard_ids, int32_t* hard_count) {
+    extern __shared__ __align__(16) float rk_q[];  // [warps per block][d4]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int d4 = ((d + 3) >> 2) << 2;
+    float* q_s = rk_q + (size_t)wib * d4;
+    const bool vec = (d % 4) == 0;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t nflag = *flag_count;
+    const double mx = (double)__ldg(max_norm_dev);
+    for (int64_t j = warp; j < nflag; j += nwarps) {
+        const int64_t i = flag_local[j];
+        const int64_t gi = base + i;
+        float f = -INFINITY, thr = -INFINITY;
+        int32_t id = -1;
+        if (lane < 2 * n_lists) {
+            const size_t off = ((size_t)i * n_lists + (lane >> 1)) * list_len + (lane & 1);
+            id = cand_id[off];
+            if (id >= 0) f = cand_score[off];
+        }
+        if (lane < n_lists) thr = cand_thr[(size_t)i * n_lists + lane];
+        float f1 = f;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            f1 = fmaxf(f1, __shfl_xor_sync(FULL, f1, off));
+            thr = fmaxf(thr, __shfl_xor_sync(FULL, thr, off));
+        }
+        const double qn2 = (double)pnorm2[gi];
+        const double qn = sqrt(qn2);
+        const double eps_s = 2.0 * (double)rel_eps * qn * mx + 2.4e-7 * (mx * mx + 2.0 * qn * mx) + 1.3e-7 * qn2 + 1e-30;
+        const double slack = 2.4e-7 * (qn2 + fabs((double)f1));
+        const bool contender = id >= 0 && (double)f >= (double)f1 - 2.0 * eps_s - slack;
+        // recorded candidates that are not contenders count as discarded rows: fold them into the bound
+        float other = (id >= 0 && !contender) ? f : -INFINITY;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) other = fmaxf(other, __shfl_xor_sync(FULL, other, off));
+        const float bound = fmaxf(thr, other);
+        unsigned todo = __ballot_sync(FULL, contender);
+        __syncwarp();
+        for (int t = lane; t < d4; t += 32) q_s[t] = t < d ? elem_f32(pts, dtype, (size_t)gi * d + t) : 0.f;
+        __syncwarp();
+        float best_d = INFINITY;
+        int32_t best_c = -1;
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int32_t c = __shfl_sync(FULL, id, src);
+            const double part = canonical_partial<true>(q_s, cent + (size_t)c * d, B2_F32, d, vec, lane);
+            const float dist = (float)butterfly_sum(part);
+            if (dist < best_d || (dist == best_d && c < best_c)) {
+                best_d = dist;
+                best_c = c;
+            }
+        }
+        bool ok = best_c >= 0 && best_d == best_d;
+        if (ok && bound > -INFINITY) ok = (qn2 * (1.0 - 1.3e-7) - (double)bound - eps_s) > (double)best_d * (1.0 + 2.4e-7) + 1e-30;
+        if (lane == 0) {
+            if (ok) assign[gi] = best_c;
+            else hard_ids[atomicAdd(hard_count, 1)] = gi;
+        }
+    }
+}
+
+__global__ void km_forward_flags_kernel(const int32_t* flag_local, const int32_t* flag_count, int64_t base, int64_t* hard_ids, int32_t* hard_count) {
+    const int64_t n = *flag_count;
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+        hard_ids[atomicAdd(hard_count, 1)] = base + flag_local[j];
 }
 
 __global__ void km_scatter_kernel(const int64_t* flag_ids, int64_t n, const int64_t* sub_assign, int64_t* assign) {
@@ -137,21 +213,29 @@ __global__ void km_count_kernel(const int64_t* assign, int64_t n, int64_t L, int
     const int64_t lo = blockIdx.x * L, hi = min(n, lo + L);
     for (int64_t i = lo + threadIdx.x; i < hi; i += 32) atomicAdd(&s_cnt[(int)assign[i]], 1);
     __syncwarp();
-    for (int c = threadIdx.x; c < k; c += 32) cnt[(size_t)blockIdx.x * k + c] = s_cnt[c];
+    for (int c = threadIdx.x; c < k; c += 32) cnt[(size_t)c * gridDim.x + blockIdx.x] = s_cnt[c];  // [k][nb]
 }
 
-// per centroid: exclusive scan of the block counts; totals[c] = cluster size
+// per centroid (one warp each): exclusive scan of its nb block counts cnt[c][0..nb); totals[c] = cluster size
 __global__ void km_scan_blocks_kernel(int32_t* cnt, int nb, int k, int32_t* totals) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int c = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
     if (c >= k) return;
+    int32_t* row = cnt + (size_t)c * nb;
     int32_t run = 0;
-#pragma unroll 8
-    for (int b = 0; b < nb; ++b) {
-        const int32_t t = cnt[(size_t)b * k + c];
-        cnt[(size_t)b * k + c] = run;
-        run += t;
+    for (int b0 = 0; b0 < nb; b0 += 32) {
+        const int b = b0 + lane;
+        const int32_t v = b < nb ? row[b] : 0;
+        int32_t incl = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int32_t o = __shfl_up_sync(FULL, incl, off);
+            if (lane >= off) incl += o;
+        }
+        if (b < nb) row[b] = run + incl - v;
+        run += __shfl_sync(FULL, incl, 31);
     }
-    totals[c] = run;
+    if (lane == 0) totals[c] = run;
 }
 
 // offsets[c] = sum of totals[0..c): one block, warp-shuffle scan over chunks of 1024 centroids
@@ -186,7 +270,7 @@ __global__ void km_fill_kernel(const int64_t* assign, int64_t n, int64_t L, int 
                                int32_t* members) {
     extern __shared__ int32_t s_run[];  // next free slot (relative to the cluster's list) for this block's points
     const int lane = threadIdx.x;
-    for (int c = lane; c < k; c += 32) s_run[c] = blk_start[(size_t)blockIdx.x * k + c];
+    for (int c = lane; c < k; c += 32) s_run[c] = blk_start[(size_t)c * gridDim.x + blockIdx.x];
     __syncwarp();
     const int64_t lo = blockIdx.x * L, hi = min(n, lo + L);
     for (int64_t base = lo; base < hi; base += 32) {
@@ -212,11 +296,11 @@ __global__ void km_fill_kernel(const int64_t* assign, int64_t n, int64_t L, int 
 // the centroids bit-identical to faiss's compute_centroids. With cent_old the same pass accumulates
 // sum_members ||x - c_old||^2 in fp64 (the iteration's objective).
 template <bool BF16>
-__global__ void __launch_bounds__(1024) km_accumulate_vec_kernel(const void* x, int d, const int64_t* ids, const int32_t* members,
+__global__ void __launch_bounds__(256) km_accumulate_vec_kernel(const void* x, int d, const int64_t* ids, const int32_t* members,
                                                                  const int64_t* offsets, const float* cent_old, float* cent_out,
                                                                  float* hassign, double* obj, int normalize) {
     constexpr int V = BF16 ? 8 : 4;
-    constexpr int U = 8;
+    constexpr int U = 16;  // member rows in flight per lane (16 x 16 B): the row gathers are latency bound
     const int c = blockIdx.x;
     const int lane = threadIdx.x & 31;
     const int vec = threadIdx.x;  // index of this lane's 16-byte column group inside a row
@@ -233,7 +317,8 @@ __global__ void __launch_bounds__(1024) km_accumulate_vec_kernel(const void* x, 
         acc[j] = 0.f;
         cold[j] = (cent_old && active) ? cent_old[(size_t)c * d + col0 + j] : 0.f;
     }
-    double dsum = 0.0;
+    double dsum = 0.0;   // objective: fp32 partial sums over the rows of one step, added up in fp64 (fp64 issue is scarce on
+    float part = 0.f;    // this part: one conversion + one add per step instead of four fp64 operations per element)
     const bool want_obj = cent_old != nullptr;
     auto consume = [&](const uint4& raw) {
         float v[V];
@@ -250,8 +335,8 @@ __global__ void __launch_bounds__(1024) km_accumulate_vec_kernel(const void* x, 
         if (want_obj) {
 #pragma unroll
             for (int j = 0; j < V; ++j) {
-                const double df = (double)v[j] - (double)cold[j];
-                dsum = fma(df, df, dsum);
+                const float df = v[j] - cold[j];
+                part = fmaf(df, df, part);
             }
         }
     };
@@ -266,6 +351,8 @@ __global__ void __launch_bounds__(1024) km_accumulate_vec_kernel(const void* x, 
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) consume(raw[u]);
+        dsum += (double)part;
+        part = 0.f;
     }
     for (; o < o1; ++o) {
         const int64_t p = members[o];
@@ -273,6 +360,7 @@ __global__ void __launch_bounds__(1024) km_accumulate_vec_kernel(const void* x, 
         const uint4 raw = active ? __ldg(xv + (size_t)r * row_vecs + vec) : make_uint4(0, 0, 0, 0);
         consume(raw);
     }
+    dsum += (double)part;
     if (active) {
         float norm = 1.f;
         if (normalize && o1 > o0) norm = __fdiv_rn(1.0f, cntf);
@@ -307,8 +395,8 @@ __global__ void km_accumulate_kernel(const void* x, int dtype, int d, const int6
                                             : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[r * d + j]);
             acc = __fadd_rn(acc, v);
             if (cent_old) {
-                const double df = (double)v - (double)cold;
-                dsum = fma(df, df, dsum);
+                const float df = v - cold;
+                dsum += (double)(df * df);
             }
         }
         if (normalize && o1 > o0) acc = __fmul_rn(acc, __fdiv_rn(1.0f, cntf));
@@ -351,23 +439,32 @@ struct DevMt19937 {
     }
 };
 
+constexpr int SPLIT_SMEM_K = 8192;  // cluster sizes are walked from shared memory up to this many centroids
+
 __global__ void __launch_bounds__(256) km_split_kernel(int d, int k, int64_t n, float* hassign, float* centroids) {
     __shared__ uint32_t s_mt[624];
     __shared__ int s_cj;
+    __shared__ float s_h[SPLIT_SMEM_K];
     int any = 0;
     for (int c = threadIdx.x; c < k; c += blockDim.x) any |= hassign[c] == 0.f;
     if (!__syncthreads_or(any)) return;
+    float* h = hassign;
+    if (k <= SPLIT_SMEM_K) {  // the rejection walk reads one size per draw: keep them next to the single drawing thread
+        for (int c = threadIdx.x; c < k; c += blockDim.x) s_h[c] = hassign[c];
+        h = s_h;
+    }
     DevMt19937 rng{s_mt, 624};
     if (threadIdx.x == 0) rng.seed(1234u);
     __syncthreads();
     const double EPS = 1 / 1024.;
+    const double denom = (double)(float)(n - k);
     for (int ci = 0; ci < k; ++ci) {
-        if (hassign[ci] != 0.f) continue;  // block-uniform (hassign is only written between barriers)
+        if (h[ci] != 0.f) continue;  // block-uniform (sizes are only written between barriers)
         if (threadIdx.x == 0) {
             int cj = 0;
             for (;; cj = (cj + 1) % k) {
                 // float p = (hassign[cj] - 1.0) / (float)(n - k);  float r = rng.rand_float();
-                const float p = (float)(((double)hassign[cj] - 1.0) / (double)(float)(n - k));
+                const float p = (float)(((double)h[cj] - 1.0) / denom);
                 const float r = __fdiv_rn(__uint2float_rn(rng.next()), 4294967296.0f);
                 if (r < p) break;
             }
@@ -383,12 +480,14 @@ __global__ void __launch_bounds__(256) km_split_kernel(int d, int k, int64_t n, 
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            const float h = hassign[cj] / 2;
-            hassign[ci] = h;
-            hassign[cj] -= h;
+            const float hv = h[cj] / 2;
+            h[ci] = hv;
+            h[cj] -= hv;
         }
         __syncthreads();
     }
+    if (h != hassign)
+        for (int c = threadIdx.x; c < k; c += blockDim.x) hassign[c] = s_h[c];
 }
 
 // searchable view of the fp32 centroid matrix; the filter operand matches the point dtype (bf16 points -> bf16 copy).
@@ -442,11 +541,21 @@ int assign_points(b2_index* idx, const void* pts, const float* pnorm2, int64_t m
     const int64_t q_pitch = round_up(d, filt_dtype == B2_F32 ? 4 : 8);
     const float rel_eps = filter_rel_eps(B2_F32, filt_dtype, idx->dtype, d);
     const bool q_in_place = idx->dtype == filt_dtype && q_pitch == d && (reinterpret_cast<uintptr_t>(pts) & 15) == 0;
-    B2_TRY(w.flag_ids.ensure((size_t)m * sizeof(int64_t)));
+    const int64_t chunk = (int64_t)1 << 23;
+    B2_TRY(w.flag_ids.ensure((size_t)std::min(m, chunk) * sizeof(int32_t)));
+    B2_TRY(w.hard_ids.ensure((size_t)m * sizeof(int64_t)));
     B2_TRY(w.flag_count.ensure(64));
     B2_TRY(w.h_count.ensure(64));
-    B2_CUDA(cudaMemsetAsync(w.flag_count.p, 0, sizeof(int32_t), st));
-    const int64_t chunk = (int64_t)1 << 23;
+    int32_t* flag_count = w.flag_count.as<int32_t>();
+    int32_t* hard_count = flag_count + 1;
+    B2_CUDA(cudaMemsetAsync(flag_count, 0, 2 * sizeof(int32_t), st));
+    const int d4 = ((d + 3) >> 2) << 2;
+    const size_t rk_smem = (size_t)8 * d4 * sizeof(float);
+    if (rk_smem > 200 * 1024) {
+        set_error("embedding dimension %d too large for the k-means re-score kernel", d);
+        return B2_ERANGE;
+    }
+    if (rk_smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(km_rescore_known_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rk_smem));
     B2_CUDA(cudaEventRecord(idx->ev0, st));
     for (int64_t q0 = 0; q0 < m; q0 += chunk) {
         const int64_t mc = std::min<int64_t>(chunk, m - q0);
@@ -464,13 +573,23 @@ int assign_points(b2_index* idx, const void* pts, const float* pnorm2, int64_t m
         B2_TRY(launch_knn_filter(cv, q_filt, q_pitch, mc, B2_METRIC_L2, kp, n_splits, two_cta, idx->cand_score.as<float>(),
                                  idx->cand_id.as<int32_t>(), idx->cand_thr.as<float>(), idx->device, st, /*top1=*/true));
         if (q0 + chunk >= m) B2_CUDA(cudaEventRecord(idx->ev1, st));
+        if (q0 > 0) B2_CUDA(cudaMemsetAsync(flag_count, 0, sizeof(int32_t), st));
         km_assign_finalize_kernel<<<(unsigned)ceil_div(mc, 256), 256, 0, st>>>(
             idx->cand_score.as<float>(), idx->cand_id.as<int32_t>(), idx->cand_thr.as<float>(), mc, 2 * n_splits, kp / 2, pnorm2,
-            cv.max_norm_dev, rel_eps, assign, w.flag_ids.as<int64_t>(), w.flag_count.as<int32_t>(), q0);
+            cv.max_norm_dev, rel_eps, assign, w.flag_ids.as<int32_t>(), flag_count, q0);
+        B2_LAUNCH_CHECK();
+        // the flagged points of this chunk, while its candidate lists are still in the workspace (count read on the device)
+        if (4 * n_splits <= 32)
+            km_rescore_known_kernel<<<dev_sms * 4, 256, rk_smem, st>>>(pts, idx->dtype, d, cent, idx->cand_score.as<float>(),
+                                                                     idx->cand_id.as<int32_t>(), idx->cand_thr.as<float>(), 2 * n_splits, kp / 2,
+                                                                     pnorm2, cv.max_norm_dev, rel_eps, w.flag_ids.as<int32_t>(), flag_count, q0,
+                                                                     assign, w.hard_ids.as<int64_t>(), hard_count);
+        else
+            km_forward_flags_kernel<<<dev_sms, 256, 0, st>>>(w.flag_ids.as<int32_t>(), flag_count, q0, w.hard_ids.as<int64_t>(), hard_count);
         B2_LAUNCH_CHECK();
     }
     int32_t* h_count = reinterpret_cast<int32_t*>(w.h_count.p);
-    B2_CUDA(cudaMemcpyAsync(h_count, w.flag_count.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaMemcpyAsync(h_count, hard_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     cudaError_t se = cudaStreamSynchronize(st);
     if (se != cudaSuccess) {
         set_error("k-means assignment failed on the device: %s", cudaGetErrorString(se));
@@ -479,18 +598,19 @@ int assign_points(b2_index* idx, const void* pts, const float* pnorm2, int64_t m
     float ms = -1.f;
     if (cudaEventElapsedTime(&ms, idx->ev0, idx->ev1) == cudaSuccess) idx->last_filter_ms = ms;
     const int64_t nf = *h_count;
-    g_stats[ST_QUERIES] += m - nf;  // (search_core counts the second-level points itself)
+    g_stats[ST_QUERIES] += m - nf;  // (search_core counts the hard points itself)
     if (n_second_level) *n_second_level = nf;
     if (nf > 0) {
-        // points the gap test could not prove: the general exact pipeline on the gathered rows
+        // points neither the gap test nor the known-contender certificate could settle (exact ties across lists, near-ties
+        // with undiscovered centroids): the general exact pipeline on the gathered rows
         const float filt_ms = idx->last_filter_ms;
         B2_TRY(w.sub.ensure((size_t)nf * d * esize(idx->dtype)));
         B2_TRY(w.sub_dis.ensure((size_t)nf * sizeof(float)));
         B2_TRY(w.sub_assign.ensure((size_t)nf * sizeof(int64_t)));
         int* err = reinterpret_cast<int*>(w.scalar.as<char>() + 16);
-        B2_TRY(launch_gather_rows(pts, idx->dtype, d, w.flag_ids.as<int64_t>(), nf, m, w.sub.p, err, st));
+        B2_TRY(launch_gather_rows(pts, idx->dtype, d, w.hard_ids.as<int64_t>(), nf, m, w.sub.p, err, st));
         B2_TRY(search_core(idx, cv, B2_METRIC_L2, w.sub.p, idx->dtype, nf, 1, nullptr, 0, w.sub_dis.as<float>(), w.sub_assign.as<int64_t>(), st));
-        km_scatter_kernel<<<(unsigned)ceil_div(nf, 256), 256, 0, st>>>(w.flag_ids.as<int64_t>(), nf, w.sub_assign.as<int64_t>(), assign);
+        km_scatter_kernel<<<(unsigned)ceil_div(nf, 256), 256, 0, st>>>(w.hard_ids.as<int64_t>(), nf, w.sub_assign.as<int64_t>(), assign);
         B2_LAUNCH_CHECK();
         idx->last_filter_ms = filt_ms;
     }
@@ -522,14 +642,14 @@ int update_centroids(b2_index* idx, const void* x, const int64_t* row_ids, int64
     B2_TRY(w.hassign.ensure((size_t)k * sizeof(float)));
     km_count_kernel<<<(unsigned)nb, 32, smem, st>>>(assign, n, L, k, w.blk.as<int32_t>());
     B2_LAUNCH_CHECK();
-    km_scan_blocks_kernel<<<(unsigned)ceil_div(k, 128), 128, 0, st>>>(w.blk.as<int32_t>(), (int)nb, k, w.totals.as<int32_t>());
+    km_scan_blocks_kernel<<<(unsigned)ceil_div(k, 8), 256, 0, st>>>(w.blk.as<int32_t>(), (int)nb, k, w.totals.as<int32_t>());
     B2_LAUNCH_CHECK();
     km_scan_totals_kernel<<<1, 1024, 0, st>>>(w.totals.as<int32_t>(), k, w.offsets.as<int64_t>());
     B2_LAUNCH_CHECK();
     km_fill_kernel<<<(unsigned)nb, 32, smem, st>>>(assign, n, L, k, w.blk.as<int32_t>(), w.offsets.as<int64_t>(), w.members.as<int32_t>());
     B2_LAUNCH_CHECK();
     const int V = idx->dtype == B2_BF16 ? 8 : 4;
-    const bool vec_ok = d % V == 0 && d / V <= 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    const bool vec_ok = d % V == 0 && d / V <= 256 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     if (vec_ok) {
         const int threads = (int)round_up(d / V, 32);
         if (idx->dtype == B2_BF16)
@@ -723,7 +843,7 @@ int b2_kmeans(b2_index* idx, const int64_t* ids, int64_t m, int32_t k, int32_t n
     const int rc = kmeans_impl(idx, ids, m, k, niter, seed, full_lloyd, out_assign, out_centroids, out_obj, w);
     cudaStreamSynchronize(idx->stream);
     // the large per-call buffers go back; the small ones stay with the handle for the next call
-    DevBuf* big[] = {&w.pts, &w.pts_norm2, &w.train, &w.train_norm2, &w.assign, &w.members, &w.flag_ids, &w.sub, &w.fin_assign, &w.ids, &w.perm};
+    DevBuf* big[] = {&w.pts, &w.pts_norm2, &w.train, &w.train_norm2, &w.assign, &w.members, &w.flag_ids, &w.hard_ids, &w.sub, &w.fin_assign, &w.ids, &w.perm};
     for (DevBuf* b : big) b->release();
     return rc;
 }

@@ -12,68 +12,16 @@
 // Canonical score (bit-for-bit what oracle/faiss_flat.c `orc_dot_canonical` / `orc_l2_canonical` compute):
 // element i is accumulated by lane (i>>2)&31 in increasing i with fp64 fma; the 32 partials are combined by
 // a 16,8,4,2,1 xor-butterfly; the double is rounded once to fp32.
+#include <cub/cub.cuh>
+
+#include "canonical.cuh"
 #include "common.cuh"
 
 namespace b2 {
 
 namespace {
 
-constexpr unsigned FULL = 0xffffffffu;
 constexpr uint64_t KEY_WORST = ~0ull;
-
-__device__ __forceinline__ double butterfly_sum(double v) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
-    return v;
-}
-
-__device__ __forceinline__ float elem_f32(const void* base, int dtype, size_t i) {
-    return dtype == B2_F32 ? reinterpret_cast<const float*>(base)[i]
-                           : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[i]);
-}
-
-// 4 consecutive elements of group g of a row (zero beyond d). `vec` = row start is 4-element aligned.
-__device__ __forceinline__ void load_group(const void* row, int dtype, int g, int d, bool vec, float (&o)[4]) {
-    const int i0 = g * 4;
-    if (vec) {
-        if (dtype == B2_F32) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(row) + g);
-            o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
-        } else {
-            const uint2 t = __ldg(reinterpret_cast<const uint2*>(row) + g);
-            o[0] = __uint_as_float(t.x << 16);
-            o[1] = __uint_as_float(t.x & 0xffff0000u);
-            o[2] = __uint_as_float(t.y << 16);
-            o[3] = __uint_as_float(t.y & 0xffff0000u);
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = (i0 + e < d) ? elem_f32(row, dtype, (size_t)(i0 + e)) : 0.f;
-    }
-}
-
-// canonical partial (this lane's share) of <q, x> or ||q - x||^2; q lives in shared memory as fp32
-template <bool IS_L2>
-__device__ __forceinline__ double canonical_partial(const float* q_s, const void* row, int dtype, int d, bool vec, int lane) {
-    double acc = 0.0;
-    const int ngroups = (d + 3) >> 2;
-    for (int g = lane; g < ngroups; g += 32) {
-        float x[4];
-        load_group(row, dtype, g, d, vec, x);
-        const float4 q4 = *reinterpret_cast<const float4*>(q_s + 4 * g);
-        const float qq[4] = {q4.x, q4.y, q4.z, q4.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            if (IS_L2) {
-                const double diff = (double)qq[e] - (double)x[e];
-                acc = fma(diff, diff, acc);
-            } else {
-                acc = fma((double)qq[e], (double)x[e], acc);
-            }
-        }
-    }
-    return acc;
-}
 
 // ---- warp-shuffle bitonic sort of 32*R u64 keys, element e = r*32 + lane, ascending ------------------------
 template <int R>
@@ -737,48 +685,33 @@ dense_select_kernel(const float* scores, int64_t n, const int32_t* q_sel, int me
     }
 }
 
-// ---- large k (> SEL_MAX_K): full sort of a dense score row ------------------------------------------------------------
-// One CTA per selected query: bitonic sort of (best-first key, tie order) over the whole row in global memory, then the
-// first k entries. faiss switches to a reservoir for k >= 100 whose tie retention at the cut is unspecified; sorted
-// truncation with the heap's order ((score desc, id desc) for IP, (dist asc, id asc) for L2) is used here. This is the
-// path of the cascade callers that ask for K = len(df) (lotus/sem_ops/sem_filter.py:486-497, sem_join.py:343-373).
-constexpr int SORT_THREADS = 1024;
-__global__ void __launch_bounds__(SORT_THREADS)
-dense_sort_kernel(const float* scores, int64_t n, int64_t npow, uint64_t* keys, const int32_t* q_sel, int metric, int k,
-                  const int64_t* id_map, int64_t id_offset, float* out_scores, int64_t* out_idx) {
-    const int s = blockIdx.x;
-    const int64_t qo = q_sel ? q_sel[s] : s;
-    const float* row = scores + (size_t)s * n;
-    uint64_t* kr = keys + (size_t)s * npow;
+// ---- large k (> SEL_MAX_K): full sort of dense score rows --------------------------------------------------------------------
+// The cascade callers ask for K = len(df) (lotus/sem_ops/sem_filter.py:486-497, sem_join.py:343-373, sem_topk.py:782-788):
+// every row is reported, best first. Keys (best-first score key << 32 | tie order) are built from the canonical scores, sorted
+// by a device-wide radix sort (CUB — library code, a plumbing step here: the scores are ours), and the first k are unpacked.
+// faiss switches to a reservoir for k >= 100 whose tie retention at the cut is unspecified; sorted truncation with the heap's
+// order ((score desc, id desc) for IP, (dist asc, id asc) for L2) is used.
+__global__ void dense_keys_kernel(const float* scores, int64_t n, int rows, int metric, uint64_t* keys) {
     const bool is_l2 = metric == B2_METRIC_L2;
-    for (int64_t j = threadIdx.x; j < npow; j += SORT_THREADS) {
-        uint64_t kk = KEY_WORST;
-        if (j < n) kk = ((uint64_t)best_first_key(row[j], metric) << 32) | (is_l2 ? (uint32_t)j : ~(uint32_t)j);
-        kr[j] = kk;
+    const int64_t total = (int64_t)rows * n;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = t % n;
+        keys[t] = ((uint64_t)best_first_key(scores[t], metric) << 32) | (is_l2 ? (uint32_t)j : ~(uint32_t)j);
     }
-    __syncthreads();
-    for (int64_t kk = 2; kk <= npow; kk <<= 1) {
-        for (int64_t j = kk >> 1; j > 0; j >>= 1) {
-            for (int64_t i = threadIdx.x; i < npow; i += SORT_THREADS) {
-                const int64_t ixj = i ^ j;
-                if (ixj > i) {
-                    const bool up = (i & kk) == 0;
-                    const uint64_t a = kr[i], b = kr[ixj];
-                    if ((a > b) == up) {
-                        kr[i] = b;
-                        kr[ixj] = a;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
+}
+
+__global__ void dense_unpack_kernel(const uint64_t* keys, int64_t n, int rows, const int32_t* q_sel, int64_t q_base, int metric, int k,
+                                    const int64_t* id_map, int64_t id_offset, float* out_scores, int64_t* out_idx) {
+    const bool is_l2 = metric == B2_METRIC_L2;
     const float pad = is_l2 ? FLT_MAX : -FLT_MAX;
-    for (int64_t o = threadIdx.x; o < k; o += SORT_THREADS) {
+    const int64_t total = (int64_t)rows * k;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = t / k, o = t - s * k;
+        const int64_t qo = q_sel ? (int64_t)q_sel[s] : q_base + s;
         float sc = pad;
         int64_t oid = -1;
         if (o < n) {
-            const uint64_t e = kr[o];
+            const uint64_t e = keys[s * n + o];
             const uint32_t lo = (uint32_t)(e & 0xffffffffu);
             const int64_t id = (int64_t)(is_l2 ? lo : ~lo);
             sc = best_first_unkey((uint32_t)(e >> 32), metric);
@@ -788,6 +721,11 @@ dense_sort_kernel(const float* scores, int64_t n, int64_t npow, uint64_t* keys, 
         out_idx[(size_t)qo * k + o] = oid;
     }
 }
+
+struct RowOffset {
+    int64_t n;
+    __host__ __device__ int64_t operator()(int64_t i) const { return i * n; }
+};
 
 // ---- k-way merge of per-shard lists -----------------------------------------------------------------------------
 template <int R>
@@ -969,11 +907,31 @@ int launch_finalize(const MatView& X, const void* q, int q_dtype, int64_t nq, in
     p.max_norm = X.max_norm;
     p.max_norm_dev = X.max_norm_dev;
     g_stats[ST_RESCORED] += nq * (int64_t)kp;
-    if (kp <= 32) return launch_finalize_r<1>(p, stream);
-    if (kp <= 64) return launch_finalize_r<2>(p, stream);
-    if (kp <= 128) return launch_finalize_r<4>(p, stream);
-    set_error("internal: finalize capacity %d", kp);
+    // survivors kept through the merge: the filter's list capacity for k <= 64; k + 32 when several splits share a large k
+    // (the 32 extra by-filter-score candidates are what the prune / certificate margins need)
+    const int need = std::max(kp, k > 64 ? k + 32 : 0);
+    if (need <= 32) return launch_finalize_r<1>(p, stream);
+    if (need <= 64) return launch_finalize_r<2>(p, stream);
+    if (need <= 128) return launch_finalize_r<4>(p, stream);
+    if (need <= 256) return launch_finalize_r<8>(p, stream);
+    if (need <= 512) return launch_finalize_r<16>(p, stream);
+    if (need <= 1024) return launch_finalize_r<32>(p, stream);
+    set_error("internal: finalize capacity %d", need);
     return B2_EINVAL;
+}
+
+// workspace bytes the full-sort path needs for `rows` score rows of length n: keys in + keys out + the sort's scratch
+size_t dense_sort_ws_bytes(int64_t rows, int64_t n) {
+    const size_t items = (size_t)rows * (size_t)n;
+    size_t temp = 0;
+    if (rows <= 4) {
+        cub::DeviceRadixSort::SortKeys(nullptr, temp, (const uint64_t*)nullptr, (uint64_t*)nullptr, (int64_t)n);
+    } else {
+        cub::CountingInputIterator<int64_t> cnt(0);
+        cub::TransformInputIterator<int64_t, RowOffset, cub::CountingInputIterator<int64_t>> beg(cnt, RowOffset{n});
+        cub::DeviceSegmentedSort::SortKeys(nullptr, temp, (const uint64_t*)nullptr, (uint64_t*)nullptr, (int64_t)items, (int64_t)rows, beg, beg + 1);
+    }
+    return 2 * items * sizeof(uint64_t) + temp + 512;
 }
 
 int launch_dense_topk(const MatView& X, const void* q, int q_dtype, int64_t nq, const int32_t* q_sel, int64_t n_sel,
@@ -981,13 +939,11 @@ int launch_dense_topk(const MatView& X, const void* q, int q_dtype, int64_t nq, 
                       int64_t dense_ws_rows, uint64_t* sort_ws, float* out_scores, int64_t* out_idx, cudaStream_t stream) {
     (void)nq;
     if (n_sel <= 0) return B2_OK;
-    const bool full_sort = k > SEL_MAX_K;  // needs sort_ws[dense_ws_rows, next_pow2(n)]
+    const bool full_sort = k > SEL_MAX_K;  // needs sort_ws of dense_sort_ws_bytes(dense_ws_rows, n)
     if (full_sort && !sort_ws) {
         set_error("internal: k=%d needs the sort workspace", k);
         return B2_EINVAL;
     }
-    int64_t npow = 1;
-    while (npow < X.n) npow <<= 1;
     const int d4 = ((X.d + 3) >> 2) << 2;
     const size_t smem = (size_t)8 * d4 * 4;
     if (smem > 48 * 1024) {
@@ -1007,13 +963,35 @@ int launch_dense_topk(const MatView& X, const void* q, int q_dtype, int64_t nq, 
                                                                                        sel, sc, metric, dense_ws);
             B2_LAUNCH_CHECK();
         }
-        float* os = q_sel ? out_scores : out_scores + (size_t)s0 * k;
-        int64_t* oi = q_sel ? out_idx : out_idx + (size_t)s0 * k;
-        if (full_sort)
-            dense_sort_kernel<<<sc, SORT_THREADS, 0, stream>>>(dense_ws, X.n, npow, sort_ws, sel, metric, k, id_map, id_offset, os, oi);
-        else
+        if (full_sort) {
+            const size_t items = (size_t)sc * (size_t)X.n;
+            uint64_t* k_in = sort_ws;
+            uint64_t* k_out = sort_ws + (size_t)dense_ws_rows * X.n;
+            void* temp = k_out + (size_t)dense_ws_rows * X.n;
+            size_t temp_bytes = dense_sort_ws_bytes(dense_ws_rows, X.n) - 2 * (size_t)dense_ws_rows * X.n * sizeof(uint64_t) - 512;
+            if (X.n > 0) {
+                dense_keys_kernel<<<grid_for((int64_t)items, 256), 256, 0, stream>>>(dense_ws, X.n, sc, metric, k_in);
+                B2_LAUNCH_CHECK();
+                if (dense_ws_rows <= 4) {
+                    for (int r = 0; r < sc; ++r)
+                        B2_CUDA(cub::DeviceRadixSort::SortKeys(temp, temp_bytes, k_in + (size_t)r * X.n, k_out + (size_t)r * X.n, (int64_t)X.n,
+                                                              0, 64, stream));
+                } else {
+                    cub::CountingInputIterator<int64_t> cnt(0);
+                    cub::TransformInputIterator<int64_t, RowOffset, cub::CountingInputIterator<int64_t>> beg(cnt, RowOffset{X.n});
+                    B2_CUDA(cub::DeviceSegmentedSort::SortKeys(temp, temp_bytes, k_in, k_out, (int64_t)items, (int64_t)sc, beg, beg + 1, stream));
+                }
+                g_stats[ST_LAUNCHES]++;
+            }
+            dense_unpack_kernel<<<grid_for((int64_t)sc * k, 256), 256, 0, stream>>>(k_out, X.n, sc, sel, s0, metric, k, id_map, id_offset,
+                                                                                  out_scores, out_idx);
+            B2_LAUNCH_CHECK();
+        } else {
+            float* os = q_sel ? out_scores : out_scores + (size_t)s0 * k;
+            int64_t* oi = q_sel ? out_idx : out_idx + (size_t)s0 * k;
             dense_select_kernel<<<sc, SEL_THREADS, 0, stream>>>(dense_ws, X.n, sel, metric, k, id_map, id_offset, os, oi);
-        B2_LAUNCH_CHECK();
+            B2_LAUNCH_CHECK();
+        }
     }
     return B2_OK;
 }

@@ -48,6 +48,7 @@ constexpr int NUM_THREADS = 224;
 constexpr int PRODUCER_WARP = 4, MMA_WARP = 5, ALLOC_WARP = 6;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_LIMIT = 232448;  // 227 KB
+constexpr int FILTER_MAX_K = 992;   // largest k served by the filter (finalize keeps k + 32 <= 1024 survivors per query)
 
 // pending (not yet merged) candidates per query row and epilogue set: a flush is triggered once any row holds
 // PEND_FLUSH of them, checked after each 8-column group, so a row never holds more than PEND_FLUSH - 1 + 8 <= PEND
@@ -1039,9 +1040,15 @@ int filter_kp_for_k(int k) {
     if (k <= 6) return 16;
     if (k <= 16) return 32;
     if (k <= 40) return 64;
-    if (k <= 64) return 96;
+    if (k <= FILTER_MAX_K) return 96;  // k > 64: several corpus splits share the load, see filter_min_splits_for_k
     return 0;
 }
+
+// k > 64 does not fit one candidate list (96 entries = 2 epilogue sets x 48 is what shared memory allows next to the operand
+// ring), so the corpus is cut into enough splits that each (split, set) sub-list expects at most ~24 of a query's top k —
+// half its capacity, 4-5 standard deviations of headroom for rows in random order. A sub-list that overflows anyway is caught
+// by the certificate (its discard bound reaches the k-th exact score) and that query takes the dense path.
+int filter_min_splits_for_k(int k) { return k <= 64 ? 1 : (int)ceil_div(k, 48); }
 
 // cta_group::2 (CTA pairs) needs at least two query tiles; B2_FILTER_2CTA=0/1 overrides the default.
 bool filter_use_pair(int64_t nq) {
@@ -1055,7 +1062,7 @@ bool filter_use_pair(int64_t nq) {
 
 // Number of corpus splits: enough work items to fill the machine, and few idle workers in the last wave.
 // In pair mode a worker is a CTA pair and a query unit is two query tiles.
-int filter_choose_splits(int64_t nq, int64_t n, int num_sms, bool two_cta, bool top1) {
+int filter_choose_splits(int64_t nq, int64_t n, int num_sms, bool two_cta, bool top1, int min_splits) {
     {
         static int forced = -1;  // B2_FILTER_SPLITS: experiments only
         if (forced < 0) {
@@ -1076,9 +1083,9 @@ int filter_choose_splits(int64_t nq, int64_t n, int num_sms, bool two_cta, bool 
     // cost model (measured, profiles/README.md): an item costs its corpus tiles plus ~13 tile-times of list warm-up, the
     // kernel takes `waves` such items back to back, and every extra split adds two candidate lists per query to finalize
     const double kWarmupTiles = top1 ? 1.0 : 13.0;  // the register-resident top-2 epilogue has no list to warm up
-    int best = 1;
     double best_cost = 1e300;
-    for (int s = 1; s <= 256 && s <= n_ntiles; ++s) {
+    int best = 0;
+    for (int s = std::max(1, min_splits); s <= 256 && s <= n_ntiles; ++s) {
         const int64_t tps = ceil_div(n_ntiles, s);
         if (ceil_div(n_ntiles, tps) != s) continue;  // every split must receive tiles
         const int64_t items = n_units * s;

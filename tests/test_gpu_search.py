@@ -204,3 +204,34 @@ def test_large_k_full_sort_path(gpu, metric):
             assert np.array_equal(bits(D[r, :m]), bits(S[r][order[:m]]))
             assert (I[r, m:] == -1).all() and (D[r, m:] == (-FMAX if metric == 0 else FMAX)).all()
     idx.close()
+
+
+# ---- k > 64: several corpus splits share the candidate lists; K = len(df): full sort (SURVEY §8f-3 cascade callers) ---------
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("k", [65, 128, 1000])
+def test_large_k_goes_through_the_filter(gpu, dtype, metric, k):
+    st = check(gpu, gauss(30_000, 64, 60 + k), gauss(200, 64, 61 + k), k, metric, dtype, expect_filter=True)
+    assert st["fallback_queries"] <= 20, st
+
+
+def test_large_k_on_a_corpus_sorted_by_topic(gpu):
+    """Rows of one topic are contiguous, so a query's best k all sit in ONE corpus split and overflow its candidate lists:
+    the certificate must notice (bound >= k-th exact score) and the dense path must answer — still exact."""
+    rng = np.random.default_rng(70)
+    centers = gauss(20, 48, 71)
+    lab = np.sort(rng.integers(0, 20, 20_000))
+    x = centers[lab] + 0.05 * gauss(20_000, 48, 72, normalize=False)
+    x = (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)
+    q = (centers[rng.integers(0, 20, 50)] + 0.05 * gauss(50, 48, 73, normalize=False)).astype(np.float32)
+    st = check(gpu, x, q, 200, 0, "bf16", expect_filter=True)
+    assert st["fallback_queries"] > 0
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_k_equal_to_the_index_size_returns_every_row_sorted(gpu, metric):
+    # sem_filter / sem_join cascade: vs(query, K=len(df)) -> all rows best first (lotus/sem_ops/sem_filter.py:486-497)
+    x, q = gauss(5000, 32, 80), gauss(3, 32, 81)
+    check(gpu, x, q, 5000, metric, "f32", expect_filter=False)
+    check(gpu, x, q[:1], 7000, metric, "bf16", expect_filter=False)      # K > n: padded with -1
+    check(gpu, grid(3000, 6, 82), grid(9, 6, 83), 3000, metric, "f32", expect_filter=False)   # ties: (score, id) heap order
