@@ -86,3 +86,58 @@ def assert_frame_matches_json(df, j):
                 assert np.float32(a) == np.float32(b), (a, b)
             else:
                 assert a == b, (a, b)
+
+
+def _nv():
+    from lotus_b200 import _native
+    return _native
+
+
+import oracle  # noqa: E402  (test infrastructure: the fake index below is the oracle behind B200VS's native calls)
+
+
+class FakeIndex:
+    """Stands in for _nv().Index: same constructor, attributes and methods, computed by the oracle."""
+    live = 0
+
+    def __init__(self, x, dtype, metric=0, device=0, on_device_ptr=None, n=None, d=None):
+        assert on_device_ptr is None
+        x = np.ascontiguousarray(x)
+        assert x.dtype == (np.float32 if dtype == _nv().F32 else np.uint16) and x.ndim == 2
+        self.raw, self.dtype, self.metric, self.device = x, dtype, metric, device
+        self.vals = x if dtype == _nv().F32 else _nv().bf16_bits_to_f32(x)
+        self.n, self.d = x.shape
+        self.closed = False
+        self.calls = []
+        FakeIndex.live += 1
+
+    def close(self):
+        if not self.closed:
+            self.closed = True
+            FakeIndex.live -= 1
+
+    def search(self, q, k, q_dtype=0, ids=None):
+        assert not self.closed
+        self.calls.append((q.dtype, q_dtype, None if ids is None else len(ids)))
+        if k > 2048:
+            raise _nv().NativeError(_nv().ERANGE, f"k={k} is not supported")
+        qv = q if q_dtype == _nv().F32 else _nv().bf16_bits_to_f32(q)
+        if ids is None:
+            return oracle.knn(self.vals, qv, k, self.metric)
+        if len(ids) and (ids.min() < 0 or ids.max() >= self.n):
+            raise _nv().NativeError(_nv().ERANGE, f"ids contains a position outside [0, {self.n})")
+        return oracle.knn_subset(self.vals, qv, k, ids, self.metric)
+
+    def gather(self, ids):
+        return self.raw[np.asarray(ids, dtype=np.int64)]
+
+    def threshold_pairs(self, thr, cap=1 << 24, part=0, nparts=1):
+        import oracle
+        pi, pj, _ = oracle.threshold_pairs(self.vals, float(thr))
+        return pi, pj
+
+    def kmeans(self, k, niter=20, seed=1234, ids=None, full_lloyd=False):
+        import oracle
+        x = self.vals if ids is None else self.vals[np.asarray(ids, dtype=np.int64)]
+        return oracle.kmeans(np.ascontiguousarray(x), k, niter=niter, full_lloyd=full_lloyd)
+

@@ -11,46 +11,10 @@ import pytest
 
 import lotus_b200 as lotus
 import oracle
-from helpers import gauss
+from helpers import FakeIndex, gauss
 from lotus_b200 import _native as nv
 from lotus_b200 import faiss_io
 from lotus_b200.vs import BF16Backed, B200VS
-
-
-class FakeIndex:
-    """Stands in for nv.Index: same constructor, attributes and methods, computed by the oracle."""
-    live = 0
-
-    def __init__(self, x, dtype, metric=nv.METRIC_IP, device=0, on_device_ptr=None, n=None, d=None):
-        assert on_device_ptr is None
-        x = np.ascontiguousarray(x)
-        assert x.dtype == (np.float32 if dtype == nv.F32 else np.uint16) and x.ndim == 2
-        self.raw, self.dtype, self.metric, self.device = x, dtype, metric, device
-        self.vals = x if dtype == nv.F32 else nv.bf16_bits_to_f32(x)
-        self.n, self.d = x.shape
-        self.closed = False
-        self.calls = []
-        FakeIndex.live += 1
-
-    def close(self):
-        if not self.closed:
-            self.closed = True
-            FakeIndex.live -= 1
-
-    def search(self, q, k, q_dtype=nv.F32, ids=None):
-        assert not self.closed
-        self.calls.append((q.dtype, q_dtype, None if ids is None else len(ids)))
-        if k > 2048:
-            raise nv.NativeError(nv.ERANGE, f"k={k} is not supported")
-        qv = q if q_dtype == nv.F32 else nv.bf16_bits_to_f32(q)
-        if ids is None:
-            return oracle.knn(self.vals, qv, k, self.metric)
-        if len(ids) and (ids.min() < 0 or ids.max() >= self.n):
-            raise nv.NativeError(nv.ERANGE, f"ids contains a position outside [0, {self.n})")
-        return oracle.knn_subset(self.vals, qv, k, ids, self.metric)
-
-    def gather(self, ids):
-        return self.raw[np.asarray(ids, dtype=np.int64)]
 
 
 @pytest.fixture
