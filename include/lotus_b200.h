@@ -113,6 +113,16 @@ B2_API int b2_index_search_dev(b2_index* idx, const void* q_dev, int64_t nq, int
 B2_API int b2_merge_topk_dev(const float* scores_dev, const int64_t* idx_dev, int32_t g, int64_t nq, int32_t k,
                       int32_t metric, int32_t device, float* out_scores_dev, int64_t* out_idx_dev, void* stream);
 
+/* The same two steps with ONE 8-byte word per entry — (float32 score bits << 32) | local row id, 0xffffffff = no result — so
+ * the row-sharded exchange is a single all-gather of nq*k*8 bytes per rank (25.6 MB at 100k x 32) instead of scores + int64 ids
+ * (38 MB in two collectives). b2_index_search_packed_dev searches the whole index and reports LOCAL ids;
+ * b2_merge_topk_packed_dev takes packed[g,nq,k] plus shard_offsets[g] (HOST array: global id of row 0 of shard s) and writes
+ * float32 scores and int64 GLOBAL ids. */
+B2_API int b2_index_search_packed_dev(b2_index* idx, const void* q_dev, int64_t nq, int32_t q_dtype, int32_t k,
+                               uint64_t* out_packed_dev, void* stream);
+B2_API int b2_merge_topk_packed_dev(const uint64_t* packed_dev, const int64_t* shard_offsets, int32_t g, int64_t nq, int32_t k,
+                             int32_t metric, int32_t device, float* out_scores_dev, int64_t* out_idx_dev, void* stream);
+
 /* ---- row gather (faiss_vs.py:38-41) ------------------------------------------------------------------ */
 /* out[m,d] in the index's dtype = x[ids]; HOST out unless out_on_device != 0 (then ids is a device pointer too) */
 B2_API int b2_index_gather(b2_index* idx, const int64_t* ids, int64_t m, void* out, int32_t out_on_device);

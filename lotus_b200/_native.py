@@ -19,7 +19,7 @@ OK, EINVAL, ENODEV, ECUDA, ENOMEM, ERANGE = 0, -1, -2, -3, -4, -5
 SYMBOLS = [
     "b2_abi_version", "b2_last_error", "b2_device_count", "b2_max_k", "b2_index_create", "b2_index_free",
     "b2_index_ntotal", "b2_index_dim", "b2_index_dtype", "b2_index_metric", "b2_index_device", "b2_index_data_dev",
-    "b2_index_search", "b2_index_search_dev", "b2_merge_topk_dev", "b2_index_gather", "b2_threshold_pairs",
+    "b2_index_search", "b2_index_search_dev", "b2_merge_topk_dev", "b2_index_search_packed_dev", "b2_merge_topk_packed_dev", "b2_index_gather", "b2_threshold_pairs",
     "b2_connected_components", "b2_kmeans", "b2_kmeans_assign", "b2_kmeans_accumulate", "b2_kmeans_assign_dev", "b2_kmeans_accumulate_dev", "b2_stats", "b2_stats_reset", "b2_last_filter_ms", "b2_host_f32_to_bf16",
 ]
 
@@ -64,6 +64,10 @@ def lib() -> ctypes.CDLL:
     L.b2_index_search_dev.argtypes = [vp, vp, i64, i32, i32, vp, i64, i64, vp, vp, vp]
     L.b2_merge_topk_dev.restype = c.c_int
     L.b2_merge_topk_dev.argtypes = [vp, vp, i32, i64, i32, i32, i32, vp, vp, vp]
+    L.b2_index_search_packed_dev.restype = c.c_int
+    L.b2_index_search_packed_dev.argtypes = [vp, vp, i64, i32, i32, vp, vp]
+    L.b2_merge_topk_packed_dev.restype = c.c_int
+    L.b2_merge_topk_packed_dev.argtypes = [vp, vp, i32, i64, i32, i32, i32, vp, vp, vp]
     L.b2_index_gather.restype = c.c_int
     L.b2_index_gather.argtypes = [vp, vp, i64, vp, i32]
     L.b2_threshold_pairs.restype = c.c_int
@@ -201,6 +205,11 @@ class Index:
                                         ctypes.c_void_p(out_scores_ptr), ctypes.c_void_p(out_idx_ptr),
                                         ctypes.c_void_p(stream) if stream else None))
 
+    def search_packed_dev(self, q_ptr: int, nq: int, k: int, q_dtype: int, out_packed_ptr: int, stream: int = 0) -> None:
+        """Whole-index search, result as one uint64 per entry (float32 score bits << 32 | local row id, 0xffffffff = none)."""
+        check(lib().b2_index_search_packed_dev(self._h, ctypes.c_void_p(q_ptr), nq, q_dtype, k, ctypes.c_void_p(out_packed_ptr),
+                                               ctypes.c_void_p(stream) if stream else None))
+
     def gather(self, ids) -> np.ndarray:
         ids = np.ascontiguousarray(ids, dtype=np.int64)
         out = np.empty((len(ids), self.d), dtype=np.float32 if self.dtype == F32 else np.uint16)
@@ -238,6 +247,15 @@ class Index:
         dist = np.empty(m, dtype=np.float32)
         check(lib().b2_kmeans_assign(self._h, _ptr(ids_a), m, _ptr(c), c.shape[0], _ptr(assign), _ptr(dist)))
         return assign, dist
+
+
+def merge_topk_packed_dev(packed_ptr: int, shard_offsets, g: int, nq: int, k: int, metric: int, device: int,
+                          out_scores_ptr: int, out_idx_ptr: int, stream: int = 0) -> None:
+    offs = np.ascontiguousarray(shard_offsets, dtype=np.int64)
+    assert len(offs) == g
+    check(lib().b2_merge_topk_packed_dev(ctypes.c_void_p(packed_ptr), _ptr(offs), g, nq, k, metric, device,
+                                         ctypes.c_void_p(out_scores_ptr), ctypes.c_void_p(out_idx_ptr),
+                                         ctypes.c_void_p(stream) if stream else None))
 
 
 def _index_kmeans_assign_dev(self, centroids_ptr: int, k: int, assign_ptr: int, dist_ptr: int = 0, ids_ptr: int = 0, m: int = 0,

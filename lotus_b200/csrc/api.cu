@@ -376,6 +376,34 @@ int b2_merge_topk_dev(const float* scores_dev, const int64_t* idx_dev, int32_t g
     return B2_OK;
 }
 
+int b2_index_search_packed_dev(b2_index* idx, const void* q_dev, int64_t nq, int32_t q_dtype, int32_t k, uint64_t* out_packed_dev,
+                               void* stream) {
+    B2_TRY(check_search_args(idx, q_dev, nq, q_dtype, k));
+    if (nq == 0) return B2_OK;
+    if (!out_packed_dev) { set_error("output buffer is NULL"); return B2_EINVAL; }
+    if (idx->n > 0xfffffffeLL) { set_error("packed lists hold 32-bit local ids"); return B2_ERANGE; }
+    DeviceGuard guard(idx->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    B2_TRY(idx->out_sc.ensure((size_t)nq * k * sizeof(float)));
+    B2_TRY(idx->out_id.ensure((size_t)nq * k * sizeof(int64_t)));
+    B2_TRY(search_core(idx, idx->view, idx->metric, q_dev, q_dtype, nq, k, nullptr, 0, idx->out_sc.as<float>(), idx->out_id.as<int64_t>(), st));
+    B2_TRY(launch_pack_topk(idx->out_sc.as<float>(), idx->out_id.as<int64_t>(), nq * (int64_t)k, out_packed_dev, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    return B2_OK;
+}
+
+int b2_merge_topk_packed_dev(const uint64_t* packed_dev, const int64_t* shard_offsets, int32_t g, int64_t nq, int32_t k, int32_t metric,
+                             int32_t device, float* out_scores_dev, int64_t* out_idx_dev, void* stream) {
+    if (g <= 0 || k <= 0 || nq < 0 || !shard_offsets) { set_error("bad merge shape g=%d nq=%lld k=%d", g, (long long)nq, k); return B2_EINVAL; }
+    if (nq == 0) return B2_OK;
+    if (!packed_dev || !out_scores_dev || !out_idx_dev) { set_error("NULL buffer"); return B2_EINVAL; }
+    DeviceGuard guard(device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    B2_TRY(launch_merge_packed(packed_dev, shard_offsets, g, nq, k, metric, out_scores_dev, out_idx_dev, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    return B2_OK;
+}
+
 int b2_index_gather(b2_index* idx, const int64_t* ids, int64_t m, void* out, int32_t out_on_device) {
     if (!idx) { set_error("Index not loaded"); return B2_EINVAL; }
     if (m < 0 || (m > 0 && (!ids || !out))) { set_error("bad gather arguments"); return B2_EINVAL; }

@@ -130,6 +130,9 @@ int launch_dense_topk(const MatView& X, const void* q, int q_dtype, int64_t nq, 
 int launch_merge_topk(const float* scores, const int64_t* idx, int g, int64_t nq, int k, int metric,
                       float* out_scores, int64_t* out_idx, cudaStream_t stream);
 size_t dense_sort_ws_bytes(int64_t rows, int64_t n);  // workspace of the full-sort path for `rows` score rows
+int launch_pack_topk(const float* scores, const int64_t* idx, int64_t total, uint64_t* out, cudaStream_t stream);
+int launch_merge_packed(const uint64_t* packed, const int64_t* shard_offsets, int g, int64_t nq, int k, int metric, float* out_scores,
+                        int64_t* out_idx, cudaStream_t stream);
 int dense_max_k();         // largest k any path supports
 int dense_select_max_k();  // largest k of the radix-select path (beyond it: full row sort)
 

@@ -48,7 +48,7 @@ constexpr int NUM_THREADS = 224;
 constexpr int PRODUCER_WARP = 4, MMA_WARP = 5, ALLOC_WARP = 6;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_LIMIT = 232448;  // 227 KB
-constexpr int FILTER_MAX_K = 992;   // largest k served by the filter (finalize keeps k + 32 <= 1024 survivors per query)
+constexpr int FILTER_MAX_K = 1000;  // largest k served by the filter (finalize keeps min(k + 32, 1024) survivors per query)
 
 // pending (not yet merged) candidates per query row and epilogue set: a flush is triggered once any row holds
 // PEND_FLUSH of them, checked after each 8-column group, so a row never holds more than PEND_FLUSH - 1 + 8 <= PEND
@@ -969,11 +969,9 @@ template <int KP, bool IS_L2, bool TF32, bool TWO, bool TOP1 = false>
 int launch_variant(const CUtensorMap& tq, const CUtensorMap& tx, const FilterParams& p, int grid, cudaStream_t stream) {
     auto kern = knn_filter_kernel<KP, IS_L2, TF32, TWO, TOP1>;
     constexpr int smem = smem_bytes(KP, TWO);
-    static bool attr_set = false;
-    if (!attr_set) {
-        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    // the attribute is per DEVICE (not per process): set it on every launch — a microsecond — so that a process driving
+    // several B200s (B200VS(device=i) for several i) launches correctly on each of them
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(TOPK_THREADS);
@@ -1254,23 +1252,19 @@ int launch_pair_filter(const MatView& X, float thr, int part, int nparts, int32_
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         if (tf32) {
-            static bool a3 = false;
-            if (!a3) { B2_CUDA(cudaFuncSetAttribute(pair_filter_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_TWO)); a3 = true; }
+            B2_CUDA(cudaFuncSetAttribute(pair_filter_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_TWO));
             B2_CUDA(cudaLaunchKernelEx(&cfg, pair_filter_kernel<true, true>, tq, tx, p));
         } else {
-            static bool a2 = false;
-            if (!a2) { B2_CUDA(cudaFuncSetAttribute(pair_filter_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_TWO)); a2 = true; }
+            B2_CUDA(cudaFuncSetAttribute(pair_filter_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_TWO));
             B2_CUDA(cudaLaunchKernelEx(&cfg, pair_filter_kernel<false, true>, tq, tx, p));
         }
     } else {
         const int grid = (int)std::min<int64_t>(items, sm_count(device));
         if (tf32) {
-            static bool a1 = false;
-            if (!a1) { B2_CUDA(cudaFuncSetAttribute(pair_filter_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM)); a1 = true; }
+            B2_CUDA(cudaFuncSetAttribute(pair_filter_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
             pair_filter_kernel<true, false><<<grid, NUM_THREADS, PAIR_SMEM, stream>>>(tq, tx, p);
         } else {
-            static bool a0 = false;
-            if (!a0) { B2_CUDA(cudaFuncSetAttribute(pair_filter_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM)); a0 = true; }
+            B2_CUDA(cudaFuncSetAttribute(pair_filter_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
             pair_filter_kernel<false, false><<<grid, NUM_THREADS, PAIR_SMEM, stream>>>(tq, tx, p);
         }
     }

@@ -44,6 +44,14 @@ class ShardedIndex:
         n, d = local_rows.shape
         self.index = nv.Index(None, self.dtype, metric, self.device, on_device_ptr=local_rows.data_ptr(), n=n, d=d)
         self.d = d
+        self.shard_offsets = np.zeros(self.world, dtype=np.int64)
+        if self.world > 1:  # global id of row 0 of every shard (the packed exchange carries local ids)
+            t = torch.tensor([self.row_offset], dtype=torch.int64, device=local_rows.device)
+            allo = torch.empty(self.world, dtype=torch.int64, device=local_rows.device)
+            dist.all_gather_into_tensor(allo, t, group=group)
+            self.shard_offsets = allo.cpu().numpy()
+        else:
+            self.shard_offsets[0] = self.row_offset
 
     def search(self, q, k: int, ids=None):
         """q: torch CUDA tensor [nq, d] (bf16 or fp32), replicated on every rank.
@@ -55,6 +63,8 @@ class ShardedIndex:
         nq = q.shape[0]
         q_dtype = nv.BF16 if q.dtype == torch.bfloat16 else nv.F32
         stream = torch.cuda.current_stream().cuda_stream
+        if ids is None and self.world > 1:
+            return self._search_packed(q, k)
         loc_s = torch.empty((nq, k), dtype=torch.float32, device=q.device)
         loc_i = torch.empty((nq, k), dtype=torch.int64, device=q.device)
         if ids is not None:
@@ -73,26 +83,68 @@ class ShardedIndex:
                                   id_offset=self.row_offset, stream=stream)
         if self.world == 1:
             return loc_s, loc_i
-        timing = os.environ.get("B2_SHARD_TIMING") == "1"
-        if timing:
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-            ev[0].record()
         all_s = torch.empty((self.world, nq, k), dtype=torch.float32, device=q.device)
         all_i = torch.empty((self.world, nq, k), dtype=torch.int64, device=q.device)
         self.dist.all_gather_into_tensor(all_s, loc_s, group=self.group)
         self.dist.all_gather_into_tensor(all_i, loc_i, group=self.group)
-        if timing:
-            ev[1].record()
         out_s = torch.empty_like(loc_s)
         out_i = torch.empty_like(loc_i)
         nv.merge_topk_dev(all_s.data_ptr(), all_i.data_ptr(), self.world, nq, k, self.metric, self.device,
                           out_s.data_ptr(), out_i.data_ptr(), stream=stream)
+        return out_s, out_i
+
+    def _search_packed(self, q, k: int):
+        """The whole-index step: local search -> ONE all-gather of 8-byte (score, local id) entries -> single-kernel k-way merge."""
+        torch = self.torch
+        nq = q.shape[0]
+        q_dtype = nv.BF16 if q.dtype == torch.bfloat16 else nv.F32
+        stream = torch.cuda.current_stream().cuda_stream
+        timing = os.environ.get("B2_SHARD_TIMING") == "1"
+        if timing:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
+        loc = torch.empty((nq, k), dtype=torch.int64, device=q.device)  # uint64 words (torch has no uint64 collectives)
+        self.index.search_packed_dev(q.data_ptr(), nq, k, q_dtype, loc.data_ptr(), stream=stream)
+        if timing:
+            ev[1].record()
+        allp = torch.empty((self.world, nq, k), dtype=torch.int64, device=q.device)
+        self.dist.all_gather_into_tensor(allp, loc, group=self.group)
         if timing:
             ev[2].record()
+        out_s = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        nv.merge_topk_packed_dev(allp.data_ptr(), self.shard_offsets, self.world, nq, k, self.metric, self.device,
+                                 out_s.data_ptr(), out_i.data_ptr(), stream=stream)
+        if timing:
+            ev[3].record()
             torch.cuda.synchronize()
-            self.last_phase_ms = {"filter": self.index.last_filter_ms(), "all_gather(+wait for slowest rank)": ev[0].elapsed_time(ev[1]),
-                                  "merge": ev[1].elapsed_time(ev[2])}
+            self.last_phase_ms = {"search (filter + finalize + pack)": ev[0].elapsed_time(ev[1]), "filter kernel": self.index.last_filter_ms(),
+                                  "all_gather (+ wait for the slowest rank)": ev[1].elapsed_time(ev[2]), "merge": ev[2].elapsed_time(ev[3])}
         return out_s, out_i
+
+    def search_host(self, q_host, k: int, out_scores_host=None, out_idx_host=None):
+        """End-to-end form: `q_host` is the (pinned) host query batch [nq, d], present in every rank's process. Each rank copies
+        only ITS 1/world slice over PCIe and the ranks all-gather the slices over NVLink; rank 0 (or every rank when the output
+        buffers are given there) copies the merged result back. Returns the device tensors (scores, idx)."""
+        torch = self.torch
+        nq = q_host.shape[0]
+        dev = torch.device("cuda", self.device)
+        if self.world == 1:
+            q = q_host.to(dev, non_blocking=True)
+        else:
+            per = -(-nq // self.world)
+            lo, hi = min(self.rank * per, nq), min((self.rank + 1) * per, nq)
+            part = torch.zeros((per, q_host.shape[1]), dtype=q_host.dtype, device=dev)
+            if hi > lo:
+                part[:hi - lo].copy_(q_host[lo:hi], non_blocking=True)
+            full = torch.empty((self.world * per, q_host.shape[1]), dtype=q_host.dtype, device=dev)
+            self.dist.all_gather_into_tensor(full, part, group=self.group)
+            q = full[:nq]
+        s, i = self.search(q, k)
+        if out_scores_host is not None:
+            out_scores_host.copy_(s, non_blocking=True)
+            out_idx_host.copy_(i, non_blocking=True)
+        return s, i
 
     def last_filter_ms(self) -> float:
         return self.index.last_filter_ms()

@@ -40,6 +40,55 @@ def build(force: bool = False) -> str:
     return _LIB
 
 
+_NATIVE = os.path.join(_HERE, "liborc_native.so")
+_native_lib = None
+_native_flags = None
+
+
+def native_lib():
+    """The same source compiled ON THIS HOST with -march=native (AVX-512 where the host has it) and fp contraction, for the TIMED
+    CPU arm only (bench.py): the portable liborc.so is built in the build container for x86-64-v3 so that it runs anywhere and
+    keeps -ffp-contract=off for the canonical scorer. Falls back to the portable library when gcc is not available here."""
+    global _native_lib, _native_flags
+    if _native_lib is not None:
+        return _native_lib
+    flags = ["-O3", "-march=native", "-mtune=native", "-ffp-contract=fast", "-funroll-loops"]
+    try:
+        import hashlib
+        cpu = ""
+        try:
+            with open("/proc/cpuinfo") as f:
+                for ln in f:
+                    if ln.startswith("flags"):
+                        cpu = ln
+                        break
+        except OSError:
+            pass
+        tag = hashlib.sha1((cpu + open(_SRC).read()).encode()).hexdigest()[:12]
+        path = os.path.join(_HERE, f"liborc_native_{tag}.so")
+        if not os.path.exists(path):
+            subprocess.run(["gcc", *flags, "-fopenmp", "-fPIC", "-shared", "-o", path, _SRC, "-lm"], check=True, capture_output=True, text=True)
+        L = ctypes.CDLL(path)
+        _native_flags = " ".join(flags)
+    except Exception:
+        L = lib()
+        _native_flags = "-O3 -march=x86-64-v3 (portable build; native build unavailable)"
+    f32p = ctypes.POINTER(ctypes.c_float)
+    i64p = ctypes.POINTER(ctypes.c_int64)
+    L.orc_knn_tiled.restype = ctypes.c_int
+    L.orc_knn_tiled.argtypes = [f32p, ctypes.c_int64, ctypes.c_int, f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, f32p, i64p]
+    L.orc_num_threads.restype = ctypes.c_int
+    L.orc_set_num_threads.argtypes = [ctypes.c_int]
+    L.orc_set_num_threads.restype = None
+    _native_lib = L
+    return L
+
+
+def native_flags() -> str:
+    native_lib()
+    return _native_flags
+
+
 _lib = None
 
 
@@ -71,6 +120,9 @@ def lib():
         L.orc_knn_blocked.restype = ctypes.c_int
         L.orc_knn_blocked.argtypes = [f32p, ctypes.c_int64, ctypes.c_int, f32p, ctypes.c_int64, ctypes.c_int,
                                       ctypes.c_int, f32p, i64p]
+        L.orc_knn_tiled.restype = ctypes.c_int
+        L.orc_knn_tiled.argtypes = [f32p, ctypes.c_int64, ctypes.c_int, f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_int, f32p, i64p]
         L.orc_threshold_pairs.restype = ctypes.c_int64
         L.orc_threshold_pairs.argtypes = [f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_float, i64p, i64p,
                                           ctypes.c_int64]
@@ -169,6 +221,73 @@ def knn_blocked(x, q, k, metric=IP):
     if rc != 0:
         raise ValueError("orc_knn_blocked failed")
     return D, I
+
+
+def knn_tiled(x, q, k, metric=IP, sb: int = 0, native: bool = True):
+    """Cache-tiled fp32 FMA search (orc_knn_tiled), by default from the -march=native build: the timed CPU arm."""
+    x, q = _f32(x), _f32(q)
+    n, d = x.shape
+    nq = q.shape[0]
+    D = np.empty((nq, k), dtype=np.float32)
+    I = np.empty((nq, k), dtype=np.int64)
+    L = native_lib() if native else lib()
+    if not hasattr(L.orc_knn_tiled, "argtypes") or L.orc_knn_tiled.argtypes is None:
+        f32p, i64p = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int64)
+        L.orc_knn_tiled.restype = ctypes.c_int
+        L.orc_knn_tiled.argtypes = [f32p, ctypes.c_int64, ctypes.c_int, f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, f32p, i64p]
+    rc = L.orc_knn_tiled(_p(x, ctypes.c_float), n, d, _p(q, ctypes.c_float), nq, k, metric, sb, _p(D, ctypes.c_float), _p(I, ctypes.c_int64))
+    if rc != 0:
+        raise ValueError("orc_knn_tiled failed")
+    return D, I
+
+
+def knn_sgemm(x, q, k, metric=IP, q_block: int = 2048, x_block: int = 65536):
+    """Second labelled CPU arm: numpy (OpenBLAS) sgemm over (query block x corpus block) + argpartition + merge — the cache
+    behaviour of faiss's BLAS path with numpy's selection instead of faiss's heap (top-k SET is the same; ties / order within
+    equal scores are numpy's). IP only needs the products; L2 adds the norms like faiss (||q||^2 + ||x||^2 - 2 q.x)."""
+    x, q = _f32(x), _f32(q)
+    n, d = x.shape
+    nq = q.shape[0]
+    kk = min(k, n)
+    D = np.full((nq, k), -np.finfo(np.float32).max if metric == IP else np.finfo(np.float32).max, dtype=np.float32)
+    I = np.full((nq, k), -1, dtype=np.int64)
+    xn = (x * x).sum(axis=1) if metric == L2 else None
+    for q0 in range(0, nq, q_block):
+        qb = q[q0:q0 + q_block]
+        qn = (qb * qb).sum(axis=1) if metric == L2 else None
+        best_s, best_i = None, None
+        for x0 in range(0, n, x_block):
+            xb = x[x0:x0 + x_block]
+            s = qb @ xb.T
+            if metric == L2:
+                s = np.maximum(qn[:, None] + xn[None, x0:x0 + x_block] - 2 * s, 0)
+                key = s
+            else:
+                key = -s
+            m = min(kk, xb.shape[0])
+            part = np.argpartition(key, m - 1, axis=1)[:, :m]
+            ps = np.take_along_axis(s, part, axis=1)
+            pi = part + x0
+            if best_s is None:
+                best_s, best_i = ps, pi
+            else:
+                cs, ci = np.concatenate([best_s, ps], axis=1), np.concatenate([best_i, pi], axis=1)
+                ck = cs if metric == L2 else -cs
+                sel = np.argpartition(ck, kk - 1, axis=1)[:, :kk]
+                best_s, best_i = np.take_along_axis(cs, sel, axis=1), np.take_along_axis(ci, sel, axis=1)
+        order = np.argsort(best_s if metric == L2 else -best_s, axis=1, kind="stable")
+        D[q0:q0 + len(qb), :best_s.shape[1]] = np.take_along_axis(best_s, order, axis=1)
+        I[q0:q0 + len(qb), :best_s.shape[1]] = np.take_along_axis(best_i, order, axis=1)
+    return D, I
+
+
+def use_all_cores_native() -> int:
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        n = os.cpu_count() or 1
+    native_lib().orc_set_num_threads(n)
+    return int(native_lib().orc_num_threads())
 
 
 def knn_subset(x, q, k, ids, metric=IP, scorer=CANONICAL):

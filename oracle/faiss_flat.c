@@ -395,6 +395,92 @@ int orc_knn_blocked(const float* x, int64_t n, int d, const float* q, int64_t nq
     return 0;
 }
 
+/* The same search, tiled for cache reuse: a thread owns a SUPER-block of `sb` x ORC_QB queries and walks the corpus in tiles of
+ * ORC_TILE_ROWS rows (a tile of 256 x 768 fp32 = 786 KB stays in the core's L2), scoring every query block of the super-block
+ * against the tile before moving on, so the corpus is streamed from memory once per super-block instead of once per 16 queries
+ * (orc_knn_blocked is memory bound on many-core hosts: 3 GB of corpus per 16 queries). Same micro-kernel, same heaps, rows still
+ * reach every heap in ascending id. This is what faiss's blocked sgemm + heap pass does at the cache level; it is the timed CPU
+ * arm of bench.py. `sb` <= 0 picks the largest super-block that still gives every thread work. */
+#define ORC_TILE_ROWS 256
+#define ORC_MAX_SB 16
+int orc_knn_tiled(const float* x, int64_t n, int d, const float* q, int64_t nq, int k, int metric, int sb, float* D, int64_t* I) {
+    if (k <= 0 || d <= 0) return -1;
+    const int is_max = metric == ORC_L2;
+    float* xn = NULL;
+    if (metric == ORC_L2) {
+        xn = (float*)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+#pragma omp parallel for
+        for (int64_t j = 0; j < n; ++j) xn[j] = dot_f32_fast(x + j * d, x + j * d, d);
+    }
+    const int64_t nblocks = (nq + ORC_QB - 1) / ORC_QB;
+    if (sb <= 0) {
+        const int64_t per_thread = nblocks / (orc_num_threads() > 0 ? orc_num_threads() : 1);
+        sb = (int)(per_thread < 1 ? 1 : (per_thread > ORC_MAX_SB ? ORC_MAX_SB : per_thread));
+    }
+    if (sb > ORC_MAX_SB) sb = ORC_MAX_SB;
+    const int64_t nsuper = (nblocks + sb - 1) / sb;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t sbi = 0; sbi < nsuper; ++sbi) {
+        const int64_t b0 = sbi * sb;
+        const int nb = (int)((nblocks - b0) < sb ? (nblocks - b0) : sb);
+        float qn[ORC_MAX_SB][ORC_QB], thresh[ORC_MAX_SB][ORC_QB], sc2[2][ORC_QB];
+        const float* qp[ORC_MAX_SB][ORC_QB];
+        int qb[ORC_MAX_SB];
+        for (int u = 0; u < nb; ++u) {
+            const int64_t q0 = (b0 + u) * ORC_QB;
+            qb[u] = (int)((nq - q0) < ORC_QB ? (nq - q0) : ORC_QB);
+            for (int t = 0; t < ORC_QB; ++t) qp[u][t] = q + (q0 + (t < qb[u] ? t : qb[u] - 1)) * d;
+            for (int t = 0; t < qb[u]; ++t) {
+                qn[u][t] = xn ? dot_f32_fast(qp[u][t], qp[u][t], d) : 0.f;
+                heap_heapify(is_max, k, D + (q0 + t) * k, I + (q0 + t) * k);
+                thresh[u][t] = D[(q0 + t) * k];
+            }
+        }
+        for (int64_t t0 = 0; t0 < n; t0 += ORC_TILE_ROWS) {
+            const int64_t t1 = (t0 + ORC_TILE_ROWS) < n ? (t0 + ORC_TILE_ROWS) : n;
+            for (int u = 0; u < nb; ++u) {
+                const int64_t q0 = (b0 + u) * ORC_QB;
+                for (int64_t j2 = t0; j2 < t1; j2 += 2) {
+                    const int nr = (t1 - j2) < 2 ? 1 : 2;
+                    const float* xj = x + j2 * d;
+                    if (nr == 2)
+                        for (int t = 0; t < ORC_QB; t += 4)
+                            dot4x2_fma(qp[u][t], qp[u][t + 1], qp[u][t + 2], qp[u][t + 3], xj, xj + d, d, sc2[0] + t, sc2[1] + t);
+                    else
+                        for (int t = 0; t < ORC_QB; t += 4) dot4_fma(qp[u][t], qp[u][t + 1], qp[u][t + 2], qp[u][t + 3], xj, d, sc2[0] + t);
+                    for (int r = 0; r < nr; ++r) {
+                        const int64_t j = j2 + r;
+                        const float* sc = sc2[r];
+                        for (int t = 0; t < qb[u]; ++t) {
+                            float s = sc[t];
+                            if (metric == ORC_L2) {
+                                s = qn[u][t] + xn[j] - 2 * s;
+                                if (s < 0) s = 0;
+                            }
+                            float* hv = D + (q0 + t) * k;
+                            int64_t* hi = I + (q0 + t) * k;
+                            if (k == 1) {
+                                if (c_cmp(is_max, hv[0], s)) {
+                                    hv[0] = s;
+                                    hi[0] = j;
+                                }
+                            } else if (c_cmp(is_max, thresh[u][t], s)) {
+                                heap_replace_top(is_max, k, hv, hi, s, j);
+                                thresh[u][t] = hv[0];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (k > 1)
+            for (int u = 0; u < nb; ++u)
+                for (int t = 0; t < qb[u]; ++t) heap_reorder(is_max, k, D + ((b0 + u) * ORC_QB + t) * k, I + ((b0 + u) * ORC_QB + t) * k);
+    }
+    free(xn);
+    return 0;
+}
+
 /* all pairs i<j with canonical IP score > thr (strict). Returns the number found; writes up to cap. */
 int64_t orc_threshold_pairs(const float* x, int64_t n, int d, float thr, int64_t* out_i, int64_t* out_j, int64_t cap) {
     int64_t cnt = 0;

@@ -138,10 +138,10 @@ def c5(args):
         e = min(n, s + (1 << 18))
         x[s:e] = (centers[lab[s:e]] + 0.5 * torch.randn((e - s, d), generator=g, device=dev)).to(torch.bfloat16)
     idx = nv.Index(None, nv.BF16, nv.METRIC_L2, 0, on_device_ptr=x.data_ptr(), n=n, d=d)
-    for full in (0, 1):
+    for full in [int(v) for v in args.c5_modes.split(",")]:
         nv.stats_reset()
         t0 = time.perf_counter()
-        a, c, obj = idx.kmeans(k, niter=20, full_lloyd=bool(full))
+        a, c, obj = idx.kmeans(k, niter=args.c5_niter, full_lloyd=bool(full))
         dt = time.perf_counter() - t0
         st = nv.stats()
         # full-size properties: the returned assignment is a fixed point of kmeans_assign on the returned centroids
@@ -154,9 +154,9 @@ def c5(args):
         clear = ((srt.values[:, 1] - srt.values[:, 0]) > 1e-6 * srt.values[:, 1]).cpu().numpy()
         amin_ok = bool((srt.indices[:, 0].cpu().numpy()[clear] == a[smp.cpu().numpy()][clear]).all())
         npts = n if full else min(n, 256 * k)
-        fl = 2.0 * npts * k * d * 20 + 2.0 * n * k * d
+        fl = 2.0 * npts * k * d * args.c5_niter + 2.0 * n * k * d
         print(json.dumps({"config": "C5 k-means %d x 768 bf16, k=1024, 20 it, %s, 1 GPU" % (n, "full Lloyd" if full else "faiss parity (256k subsample)"),
-                          "seconds": dt, "s_per_iteration": dt / 21, "assign_tflops_equiv": fl / dt / 1e12, "obj_first": float(obj[0]),
+                          "seconds": dt, "s_per_iteration": dt / (args.c5_niter + 1), "assign_tflops_equiv": fl / dt / 1e12, "obj_first": float(obj[0]),
                           "obj_last": float(obj[-1]), "clusters_used": int(len(np.unique(a))), "assign_is_fixed_point": idem,
                           "assign_equals_fp64_argmin_4096_sample": amin_ok, "fallback_queries": st["fallback_queries"],
                           "launches": st["launches"]}), flush=True)
@@ -172,6 +172,8 @@ if __name__ == "__main__":
     ap.add_argument("--dedup-part", type=int, default=0)
     ap.add_argument("--dedup-parts", type=int, default=1, help="time one rank's share of the upper-triangular tile grid (8 = C4's 8-GPU split)")
     ap.add_argument("--no-warmup", action="store_true")
+    ap.add_argument("--c5-modes", default="0,1", help="0 = faiss parity (256*k subsample), 1 = full Lloyd")
+    ap.add_argument("--c5-niter", type=int, default=20)
     a = ap.parse_args()
     for w in a.which.split(","):
         {"c2": c2, "c4": c4, "c5": c5}[w](a)
