@@ -179,7 +179,8 @@ B2_API int b2_host_f32_to_bf16(const float* x, int64_t count, uint16_t* out, int
 
 /* ---- instrumentation ---------------------------------------------------------------------------------- */
 /* counters since the last b2_stats_reset(): [0] kernels launched by this library, [1] queries answered,
- * [2] queries that took the exact dense fallback, [3] tcgen05 filter launches, [4] rows rescored exactly.
+ * [2] queries that took the exact dense fallback, [3] tcgen05 filter launches, [4] rows rescored exactly,
+ * [5] queries of fp32 indexes that the bf16 first-level filter could not certify and the tf32 level answered.
  * Returns how many counters were written (<= cap). */
 B2_API int b2_stats(int64_t* out, int32_t cap);
 B2_API void b2_stats_reset(void);

@@ -113,7 +113,7 @@ def stats() -> dict:
     buf = (ctypes.c_int64 * 8)()
     lib().b2_stats(buf, 8)
     return {"launches": buf[0], "queries": buf[1], "fallback_queries": buf[2], "filter_launches": buf[3],
-            "rescored_rows": buf[4]}
+            "rescored_rows": buf[4], "second_level_queries": buf[5]}
 
 
 def stats_reset() -> None:

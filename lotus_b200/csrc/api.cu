@@ -33,7 +33,7 @@ namespace b2 {
 
 // Build the searchable view of a row-major matrix that already sits in device memory.
 int build_view(const void* store, int64_t n, int d, int dtype, DevBuf& filt_pad, DevBuf& norm2, DevBuf& scalar,
-                      MatView& v, cudaStream_t st) {
+                      MatView& v, cudaStream_t st, DevBuf* filt16) {
     v.store = store;
     v.n = n;
     v.d = d;
@@ -48,6 +48,15 @@ int build_view(const void* store, int64_t n, int d, int dtype, DevBuf& filt_pad,
         B2_TRY(filt_pad.ensure((size_t)std::max<int64_t>(n, 1) * v.filt_pitch * esize(dtype)));
         B2_TRY(launch_convert_pad(store, dtype, n, d, filt_pad.p, dtype, v.filt_pitch, st));
         v.filt = filt_pad.p;
+    }
+    v.filt16 = nullptr;
+    v.filt16_pitch = 0;
+    static const bool bf16_first = [] { const char* e = getenv("B2_F32_BF16_FIRST"); return e ? atoi(e) != 0 : true; }();
+    if (filt16 && dtype == B2_F32 && bf16_first && n >= 4096) {
+        v.filt16_pitch = round_up(d, 8);
+        B2_TRY(filt16->ensure((size_t)n * v.filt16_pitch * 2));
+        B2_TRY(launch_convert_pad(store, dtype, n, d, filt16->p, B2_BF16, v.filt16_pitch, st));
+        v.filt16 = filt16->p;
     }
     B2_TRY(norm2.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(float)));
     B2_TRY(scalar.ensure(64));
@@ -77,6 +86,22 @@ float filter_rel_eps(int store_dtype, int filt_dtype, int q_dtype, int d) {
     return (float)(acc + ex + eq + ex * eq + 1e-6);
 }
 
+// deferred[j] = base + sel[j] (chunk-local query numbers -> batch-wide)
+__global__ void defer_append_kernel(const int32_t* sel, int64_t n, int64_t base, int64_t* deferred) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j < n) deferred[j] = base + sel[j];
+}
+
+// out[rows[j], :] = sub[j, :] for the k-wide result rows of the deferred queries
+__global__ void scatter_rows_kernel(const int64_t* rows, int64_t n, int k, const float* sub_sc, const int64_t* sub_id, float* out_sc,
+                                    int64_t* out_id) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n * k) return;
+    const int64_t j = t / k, o = t - j * k;
+    out_sc[rows[j] * k + o] = sub_sc[t];
+    out_id[rows[j] * k + o] = sub_id[t];
+}
+
 __global__ void fill_pad_kernel(float* sc, int64_t* id, int64_t total, float pad) {
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         sc[t] = pad;
@@ -84,17 +109,30 @@ __global__ void fill_pad_kernel(float* sc, int64_t* id, int64_t total, float pad
     }
 }
 
-int search_core(b2_index* idx, const MatView& X, int metric, const void* q_dev, int q_dtype, int64_t nq, int k,
-                       const int64_t* id_map, int64_t id_offset, float* out_sc, int64_t* out_id, cudaStream_t st) {
-    idx->last_filter_ms = -1.f;
+// level 0: the caller's search. For an fp32 store with a bf16 copy (X.filt16) and a small k it is the FIRST level of a two-level
+// search: bf16 filter with a longer candidate list, the queries whose certificate fails are deferred, gathered and answered by
+// a level-1 call (tf32 filter on the same store, then the dense path for what still fails) and scattered back.
+int search_core(b2_index* idx, const MatView& X_in, int metric, const void* q_dev, int q_dtype, int64_t nq, int k,
+                       const int64_t* id_map, int64_t id_offset, float* out_sc, int64_t* out_id, cudaStream_t st, int level) {
+    if (level == 0) idx->last_filter_ms = -1.f;
     if (nq <= 0) return B2_OK;
-    g_stats[ST_QUERIES] += nq;
+    if (level == 0) g_stats[ST_QUERIES] += nq;
+    // candidate capacity of the bf16 first level (the 2^-8 operand error lets more rows straddle the k-th score): 0 = not used
+    const int kp16 = (X_in.filt16 && level == 0 && X_in.n >= 4096) ? (k <= 4 ? 32 : k <= 12 ? 64 : k <= 24 ? 96 : 0) : 0;
+    MatView X = X_in;
+    if (kp16) {
+        X.filt = X_in.filt16;
+        X.filt_pitch = X_in.filt16_pitch;
+        X.filt_dtype = B2_BF16;
+    }
+    const bool defer = kp16 != 0;
+    int64_t n_deferred = 0;
     if (X.n <= 0) {
         fill_pad_kernel<<<148, 256, 0, st>>>(out_sc, out_id, nq * k, metric == B2_METRIC_L2 ? FLT_MAX : -FLT_MAX);
         B2_LAUNCH_CHECK();
         return B2_OK;
     }
-    const int kp = filter_kp_for_k(k);
+    const int kp = kp16 ? kp16 : filter_kp_for_k(k);
     const int min_splits = filter_min_splits_for_k(k);
     // the filter needs a corpus worth tiling: two tiles at least, and for k > 64 enough tiles to cut into min_splits splits
     // with k well below the rows of a split
@@ -167,7 +205,12 @@ int search_core(b2_index* idx, const MatView& X, int metric, const void* q_dev, 
             idx->last_filter_ms = (idx->last_filter_ms < 0 ? 0.f : idx->last_filter_ms) + ms;
         // exact fallback for the queries the certificate could not cover
         const int64_t n_sel = *h_count;
-        if (n_sel > 0) {
+        if (n_sel > 0 && defer) {
+            B2_TRY(idx->defer.ensure((size_t)nq * sizeof(int64_t)));
+            defer_append_kernel<<<(unsigned)ceil_div(n_sel, 256), 256, 0, st>>>(sel_list, n_sel, q0, idx->defer.as<int64_t>() + n_deferred);
+            B2_LAUNCH_CHECK();
+            n_deferred += n_sel;
+        } else if (n_sel > 0) {
             if (k > dense_max_k()) {
                 set_error("internal: fallback with k=%d", k);
                 return B2_ERANGE;
@@ -178,6 +221,24 @@ int search_core(b2_index* idx, const MatView& X, int metric, const void* q_dev, 
             B2_TRY(launch_dense_topk(X, qc, q_dtype, nqc, sel_list, n_sel, metric, k, id_map, id_offset, idx->dense.as<float>(), rows,
                                      nullptr, osc, oid, st));
         }
+    }
+    if (n_deferred > 0) {
+        // second level: the deferred queries against the exact-operand (tf32) filter of the same store
+        const size_t qrow = (size_t)X.d * esize(q_dtype);
+        B2_TRY(idx->q_sub.ensure((size_t)n_deferred * qrow));
+        B2_TRY(idx->sub_sc.ensure((size_t)n_deferred * k * sizeof(float)));
+        B2_TRY(idx->sub_id.ensure((size_t)n_deferred * k * sizeof(int64_t)));
+        B2_TRY(idx->scalar.ensure(64));
+        int* err = reinterpret_cast<int*>(idx->scalar.as<char>() + 16);
+        B2_TRY(launch_gather_rows(q_dev, q_dtype, X.d, idx->defer.as<int64_t>(), n_deferred, nq, idx->q_sub.p, err, st));
+        MatView X2 = X_in;
+        X2.filt16 = nullptr;
+        B2_TRY(search_core(idx, X2, metric, idx->q_sub.p, q_dtype, n_deferred, k, id_map, id_offset, idx->sub_sc.as<float>(),
+                           idx->sub_id.as<int64_t>(), st, /*level=*/1));
+        scatter_rows_kernel<<<(unsigned)ceil_div(n_deferred * k, 256), 256, 0, st>>>(idx->defer.as<int64_t>(), n_deferred, k, idx->sub_sc.as<float>(),
+                                                                                    idx->sub_id.as<int64_t>(), out_sc, out_id);
+        B2_LAUNCH_CHECK();
+        g_stats[ST_SECOND_LEVEL] += n_deferred;
     }
     return B2_OK;
 }
@@ -196,7 +257,7 @@ static int build_subset(b2_index* idx, const int64_t* ids_dev, int64_t m, MatVie
         set_error("ids contains a position outside [0, %lld)", (long long)idx->n);
         return B2_ERANGE;
     }
-    return build_view(idx->sub_store.p, m, idx->d, idx->dtype, idx->sub_filt, idx->sub_norm2, idx->scalar, sub, st);
+    return build_view(idx->sub_store.p, m, idx->d, idx->dtype, idx->sub_filt, idx->sub_norm2, idx->scalar, sub, st, &idx->sub_filt16);
 }
 
 }  // namespace b2
@@ -268,7 +329,7 @@ int b2_index_create(const void* x, int64_t n, int32_t d, int32_t dtype, int32_t 
                                         x_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, idx->stream);
         if (e != cudaSuccess) { set_error("copy of the matrix failed: %s", cudaGetErrorString(e)); return fail(B2_ECUDA); }
     }
-    rc = build_view(idx->store.p, n, d, dtype, idx->filt_pad, idx->norm2, idx->scalar, idx->view, idx->stream);
+    rc = build_view(idx->store.p, n, d, dtype, idx->filt_pad, idx->norm2, idx->scalar, idx->view, idx->stream, &idx->filt16);
     if (rc != B2_OK) return fail(rc);
     *out = idx;
     return B2_OK;
@@ -277,7 +338,7 @@ int b2_index_create(const void* x, int64_t n, int32_t d, int32_t dtype, int32_t 
 void b2_index_free(b2_index* idx) {
     if (!idx) return;
     DeviceGuard guard(idx->device);
-    DevBuf* bufs[] = {&idx->store, &idx->filt_pad, &idx->norm2, &idx->scalar, &idx->q_in, &idx->q_filt, &idx->cand_score,
+    DevBuf* bufs[] = {&idx->store, &idx->filt_pad, &idx->filt16, &idx->sub_filt16, &idx->defer, &idx->q_sub, &idx->sub_sc, &idx->sub_id, &idx->norm2, &idx->scalar, &idx->q_in, &idx->q_filt, &idx->cand_score,
                       &idx->cand_id, &idx->cand_thr, &idx->flags, &idx->sel, &idx->dense, &idx->out_sc, &idx->out_id,
                       &idx->ids_dev, &idx->sub_store, &idx->sub_filt, &idx->sub_norm2, &idx->sort_keys};
     for (DevBuf* b : bufs) b->release();

@@ -16,7 +16,7 @@ namespace b2 {
 // ---- error plumbing ------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 extern int64_t g_stats[8];
-enum { ST_LAUNCHES = 0, ST_QUERIES = 1, ST_FALLBACK = 2, ST_FILTER_LAUNCHES = 3, ST_RESCORED = 4 };
+enum { ST_LAUNCHES = 0, ST_QUERIES = 1, ST_FALLBACK = 2, ST_FILTER_LAUNCHES = 3, ST_RESCORED = 4, ST_SECOND_LEVEL = 5 };
 
 #define B2_CUDA(expr)                                                                              \
     do {                                                                                           \
@@ -90,6 +90,11 @@ struct MatView {
     int32_t dtype = B2_F32;       // element type of `store`
     int32_t filt_dtype = B2_F32;  // element type of `filt`: B2_BF16 -> kind::f16 MMA, B2_F32 -> kind::tf32 MMA
     int64_t filt_pitch = 0;  // elements
+    // fp32 stores only (optional): a bf16 rounding of the rows, pitch multiple of 8. When present, searches run a FIRST level on it
+    // (kind::f16 at twice the tf32 rate, operand error 2^-8 per fp32 operand in the certificate) and only the queries whose
+    // certificate fails there go through the tf32 filter on `filt`.
+    const void* filt16 = nullptr;
+    int64_t filt16_pitch = 0;
     float max_norm = 0.f;    // max_j ||x_j|| (upper bound), for the certification margin
     const float* max_norm_dev = nullptr;  // when set, the kernels read the bound from device memory instead (no host sync:
                                           // the k-means loop rebuilds its centroid view every iteration)

@@ -84,11 +84,12 @@ struct b2_index {
     int32_t d = 0;
     int32_t dtype = B2_F32;
     int32_t metric = B2_METRIC_IP;
-    DevBuf store, filt_pad, norm2, scalar;
+    DevBuf store, filt_pad, filt16, norm2, scalar;
     MatView view;
     // per-call workspaces
     DevBuf q_in, q_filt, cand_score, cand_id, cand_thr, flags, sel, dense, out_sc, out_id, ids_dev;
-    DevBuf sub_store, sub_filt, sub_norm2, sort_keys;
+    DevBuf sub_store, sub_filt, sub_filt16, sub_norm2, sort_keys;
+    DevBuf defer, q_sub, sub_sc, sub_id;  // two-level search of fp32 indexes: deferred queries, their rows and results
     HostBuf h_flags;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -102,10 +103,10 @@ static inline size_t esize(int dtype) { return dtype == B2_F32 ? 4 : 2; }
 
 // searchable view (filter operand, row norms, max norm) of a row-major device matrix
 int build_view(const void* store, int64_t n, int d, int dtype, DevBuf& filt_pad, DevBuf& norm2, DevBuf& scalar, MatView& v,
-               cudaStream_t st);
+               cudaStream_t st, DevBuf* filt16 = nullptr);
 // the exact top-k pipeline on device buffers: tcgen05 filter -> finalize/certify -> dense fallback
 int search_core(b2_index* idx, const MatView& X, int metric, const void* q_dev, int q_dtype, int64_t nq, int k,
-                const int64_t* id_map, int64_t id_offset, float* out_sc, int64_t* out_id, cudaStream_t st);
+                const int64_t* id_map, int64_t id_offset, float* out_sc, int64_t* out_id, cudaStream_t st, int level = 0);
 float filter_rel_eps(int store_dtype, int filt_dtype, int q_dtype, int d);
 
 }  // namespace b2

@@ -105,8 +105,88 @@ def _to_host_matrix(a: Any, want_bf16: bool, exact_bf16_ok: bool = False):
     return f, nv.F32, f
 
 
+class MultiDeviceIndex:
+    """Row-sharded flat index over several B200s driven from ONE process (for users who do not run under torchrun; under
+    torchrun use lotus_b200.distributed.ShardedIndex, whose exchange runs over NCCL/NVLink). Shard g holds the contiguous rows
+    `shard_bounds(n, G, g)` on devices[g]; a search runs the G per-device C-ABI calls concurrently (ctypes releases the GIL),
+    then merges the G sorted lists on the host with the same (score, shard order) rule as the k-way merge kernel.
+    Same surface as `_native.Index` as far as B200VS uses it."""
+
+    def __init__(self, host_matrix: np.ndarray, code: int, metric: int, devices: list[int]):
+        from concurrent.futures import ThreadPoolExecutor
+        from .distributed import shard_bounds
+        self.devices = list(devices)
+        self.n, self.d = host_matrix.shape
+        self.dtype, self.metric, self.device = code, metric, self.devices[0]
+        self.bounds = [shard_bounds(self.n, len(self.devices), g) for g in range(len(self.devices))]
+        self.pool = ThreadPoolExecutor(max_workers=len(self.devices))
+        self.shards = list(self.pool.map(lambda gb: nv.Index(np.ascontiguousarray(host_matrix[gb[1][0]:gb[1][1]]), code, metric, gb[0]),
+                                         zip(self.devices, self.bounds)))
+        self._host = host_matrix  # kept for the operators that need the whole matrix on one device (dedup, k-means)
+        self._replica: nv.Index | None = None
+
+    def search(self, q: np.ndarray, k: int, q_dtype: int = nv.F32, ids: np.ndarray | None = None):
+        def one(g):
+            lo, hi = self.bounds[g]
+            if ids is None:
+                D, I = self.shards[g].search(q, k, q_dtype)
+            else:
+                mine = ids[(ids >= lo) & (ids < hi)] - lo
+                if len(mine) == 0:
+                    pad = np.finfo(np.float32).max if self.metric == nv.METRIC_L2 else -np.finfo(np.float32).max
+                    return np.full((len(q), k), pad, np.float32), np.full((len(q), k), -1, np.int64)
+                D, I = self.shards[g].search(q, k, q_dtype, ids=np.ascontiguousarray(mine))
+            return D, np.where(I >= 0, I + lo, -1)
+        if ids is not None and len(ids) and (ids.min() < 0 or ids.max() >= self.n):
+            raise nv.NativeError(nv.ERANGE, f"ids contains a position outside [0, {self.n})")
+        parts = list(self.pool.map(one, range(len(self.shards))))
+        return merge_shard_lists([p[0] for p in parts], [p[1] for p in parts], self.metric)
+
+    def gather(self, ids) -> np.ndarray:
+        ids = np.asarray(ids, dtype=np.int64)
+        if len(ids) and (ids.min() < 0 or ids.max() >= self.n):
+            raise nv.NativeError(nv.ERANGE, f"ids contains a position outside [0, {self.n})")
+        out = np.empty((len(ids), self.d), dtype=np.float32 if self.dtype == nv.F32 else np.uint16)
+        for g, (lo, hi) in enumerate(self.bounds):
+            m = (ids >= lo) & (ids < hi)
+            if m.any():
+                out[m] = self.shards[g].gather(ids[m] - lo)
+        return out
+
+    def _whole(self) -> "nv.Index":
+        if self._replica is None:  # all-pairs dedup and k-means want the whole matrix on one device
+            self._replica = nv.Index(np.ascontiguousarray(self._host), self.dtype, self.metric, self.devices[0])
+        return self._replica
+
+    def threshold_pairs(self, thr: float, **kw):
+        return self._whole().threshold_pairs(thr, **kw)
+
+    def kmeans(self, k: int, **kw):
+        return self._whole().kmeans(k, **kw)
+
+    def close(self) -> None:
+        for s in self.shards:
+            s.close()
+        if self._replica is not None:
+            self._replica.close()
+        self.pool.shutdown(wait=False)
+
+
+def merge_shard_lists(D_parts: list, I_parts: list, metric: int):
+    """Host k-way merge of per-shard (score, global id) lists [nq, k] -> [nq, k]: best first; equal scores keep each shard's
+    (already faiss-ordered) list order, lower shards first for L2, higher shards first for IP — the rule of merge_topk_kernel."""
+    g = len(D_parts)
+    order = range(g) if metric == nv.METRIC_L2 else range(g - 1, -1, -1)
+    D = np.concatenate([D_parts[i] for i in order], axis=1)
+    I = np.concatenate([I_parts[i] for i in order], axis=1)
+    k = D_parts[0].shape[1]
+    key = np.where(I >= 0, D if metric == nv.METRIC_L2 else -D, np.inf)
+    sel = np.argsort(key, axis=1, kind="stable")[:, :k]
+    return np.take_along_axis(D, sel, axis=1), np.take_along_axis(I, sel, axis=1)
+
+
 class B200VS(VS):
-    """Flat (brute-force, exact) vector store on one B200.
+    """Flat (brute-force, exact) vector store on one B200 (or, with devices=[...], row-sharded over several from one process).
 
     Args mirror FaissVS(factory_string="Flat", metric=faiss.METRIC_INNER_PRODUCT) (faiss_vs.py:14).
     dtype: "f32" (store what faiss would: float32), "bf16" (round the corpus to bfloat16 once; exact search
@@ -116,7 +196,7 @@ class B200VS(VS):
     accepts_id_arrays = True  # `ids=` may be a numpy int64 array (the operators then skip building a Python list)
 
     def __init__(self, factory_string: str = "Flat", metric: int = METRIC_INNER_PRODUCT, dtype: str = "auto",
-                 device: int = 0, cache_size: int = 4):
+                 device: int = 0, cache_size: int = 4, devices: "list[int] | None" = None):
         super().__init__()
         if factory_string != "Flat":
             raise ValueError(f"B200VS implements the flat (exact) index only; factory_string={factory_string!r}")
@@ -127,7 +207,8 @@ class B200VS(VS):
         self.factory_string = factory_string
         self.metric = metric
         self.dtype = dtype
-        self.device = device
+        self.devices = list(devices) if devices else None
+        self.device = self.devices[0] if self.devices else device
         self.index_dir: str | None = None
         self.b2_index: nv.Index | None = None
         self.vecs: Any = None
@@ -138,6 +219,13 @@ class B200VS(VS):
     def _build(self, embeddings: Any) -> nv.Index:
         nv.require_device()
         t = _cuda_tensor(embeddings)
+        if self.devices and len(self.devices) > 1:
+            want16 = self.dtype == "bf16"
+            if t is not None:
+                import torch
+                want16 = want16 or (self.dtype == "auto" and t.dtype == torch.bfloat16)
+            host, code, _ = _to_host_matrix(embeddings, want16)
+            return MultiDeviceIndex(host, code, self.metric, self.devices)  # type: ignore[return-value]
         if t is not None and t.dim() == 2 and t.device.index == self.device:
             # device hand-off: the encoder's output never visits the host on its way into the index
             import torch
@@ -225,7 +313,7 @@ class B200VS(VS):
             raise ValueError("Index not loaded")
         ids_a = None if ids is None else np.asarray(list(ids) if not isinstance(ids, np.ndarray) else ids, dtype=np.int64)
         t = _cuda_tensor(query_vectors)
-        if t is not None and ids_a is None and t.dim() == 2 and t.device.index == self.device:
+        if t is not None and ids_a is None and t.dim() == 2 and t.device.index == self.device and not isinstance(self.b2_index, MultiDeviceIndex):
             return self._call_device(t, int(K))
         q, code, _ = _to_host_matrix(query_vectors, False, exact_bf16_ok=self.b2_index.dtype == nv.BF16)
         if q.shape[1] != self.b2_index.d:

@@ -72,6 +72,27 @@ def test_sem_search_on_gpu(env):
     assert list(out.index) == Is[0].tolist()
 
 
+def test_baseline_config0_sem_sim_join_two_1k_frames_384d_fp32_k5(env):
+    """BASELINE.json configs[0] at its stated shape: sem_sim_join on two 1k-row DataFrames, precomputed 384-d fp32 embeddings,
+    K=5 — the GPU operator against the oracle-backed join (indices exact, scores bit-exact), both frames indexed."""
+    _, vs, tmp = env
+    table = {}
+    xl, xr = gauss(1000, 384, 90), gauss(1000, 384, 91)
+    for i in range(1000):
+        table[f"left {i}"], table[f"right {i}"] = xl[i], xr[i]
+    lotus.settings.configure(rm=lotus.TableRM(table))
+    left = pd.DataFrame({"a": [f"left {i}" for i in range(1000)]}).sem_index("a", str(tmp / "c0l"))
+    right = pd.DataFrame({"b": [f"right {i}" for i in range(1000)]}).sem_index("b", str(tmp / "c0r"))
+    got = left.sem_sim_join(right, "a", "b", K=5)
+    D, I = oracle.knn(xr, xl, 5)
+    assert len(got) == 5000 and list(got.columns) == ["a", "_scores", "b"]
+    assert got["b"].tolist() == [f"right {i}" for i in I.reshape(-1)]
+    assert np.array_equal(bits(got["_scores"].to_numpy(np.float32)), bits(D.reshape(-1)))
+    assert list(got.index) == np.repeat(np.arange(1000), 5).tolist()
+    many = right.sem_search("b", ["left 3", "left 4"], K=5, return_scores=True)   # multi-query search, one device call
+    assert [list(f.index) for f in many] == [I[3].tolist(), I[4].tolist()]
+
+
 def planted(n, d, seed, frac=0.05):
     x = gauss(n, d, seed)
     rng = np.random.default_rng(seed + 1)

@@ -179,6 +179,36 @@ def test_sem_search_topk_scores_and_filtered_frames(env):
         df.sem_search("t", q, K=2, n_rerank=1)
 
 
+def test_sem_search_multi_query_equals_the_single_query_calls(env):
+    # one batched vs() call for a list of queries; every frame equals its single-query counterpart
+    rm, vs, tmp = env
+    df = pd.DataFrame({"t": [f"doc{i}" for i in range(40)]}).sem_index("t", str(tmp / "m"))
+    qs = ["doc3", "doc17", "something else"]
+    calls = []
+    orig = type(vs).__call__
+
+    def counting(self, *a, **kw):
+        calls.append(1)
+        return orig(self, *a, **kw)
+
+    type(vs).__call__ = counting
+    try:
+        many = df.sem_search("t", qs, K=5, return_scores=True)
+        assert len(calls) == 1 and isinstance(many, list) and len(many) == 3
+        sub = df[df.index % 2 == 1]
+        many_sub = sub.sem_search.batch("t", qs, K=4, return_scores=True)
+    finally:
+        type(vs).__call__ = orig
+    for q, got in zip(qs, many):
+        pd.testing.assert_frame_equal(got, df.sem_search("t", q, K=5, return_scores=True))
+    for q, got in zip(qs, many_sub):
+        pd.testing.assert_frame_equal(got, sub.sem_search("t", q, K=4, return_scores=True))
+    vecs = rm(qs)                                            # precomputed query vectors [Q, d]
+    for a, b in zip(df.sem_search("t", vecs, K=5), many):
+        assert list(a.index) == list(b.index)
+    assert [len(f) for f in df.iloc[0:0].sem_search("t", qs, K=3)] == [0, 0, 0]
+
+
 def test_cluster_fn_validation(env):
     # lotus/utils.py:35-39,49-52
     from lotus_b200.utils import cluster

@@ -178,3 +178,32 @@ def test_get_vectors_from_index_does_not_switch_the_loaded_index(fake_native, tm
     vs2.load_index(da)
     assert np.array_equal(vs2.get_vectors_from_index(db, [1]), xb[[1]]) and vs2.index_dir == da
     assert np.array_equal(vs2(xa[:1], 1).indices, [[0]])
+
+
+def test_single_process_multi_device_store_merges_like_the_kernel(fake_native, tmp_path):
+    """B200VS(devices=[...]): rows sharded over several devices driven from one process; per-device searches + host k-way merge
+    must equal the single-index answer (including the ids= subset form and row gathers across shards)."""
+    from lotus_b200.vs import MultiDeviceIndex, merge_shard_lists
+    x, q = gauss(301, 16, 31), gauss(9, 16, 32)
+    for metric, om in ((faiss_io.METRIC_INNER_PRODUCT, oracle.IP), (faiss_io.METRIC_L2, oracle.L2)):
+        vs = B200VS(metric=metric, devices=[0, 1, 2])
+        d = str(tmp_path / f"md{metric}")
+        vs.index(None, x, d)
+        assert isinstance(vs.b2_index, MultiDeviceIndex) and [s.device for s in vs.b2_index.shards] == [0, 1, 2]
+        out = vs(q, 7)
+        D, I = oracle.knn(x, q, 7, om)
+        assert np.array_equal(out.indices, I) and np.array_equal(out.distances, D)
+        ids = np.arange(3, 301, 4)
+        out = vs(q, 5, ids=ids)
+        Ds, Is = oracle.knn_subset(x, q, 5, ids, om)
+        assert np.array_equal(out.indices, Is) and np.array_equal(out.distances, Ds)
+        assert np.array_equal(vs.get_vectors_from_index(d, [300, 0, 150]), x[[300, 0, 150]])
+        out = vs(q, 400)                                     # K > n: padded
+        assert (np.asarray(out.indices)[:, 301:] == -1).all() and np.array_equal(np.asarray(out.indices)[:, :301], oracle.knn(x, q, 301, om)[1])
+        vs.close()
+    # exact ties across shards: L2 keeps the lower shard first, IP the higher shard first (merge_topk_kernel's rule)
+    s = [np.full((1, 2), 0.5, np.float32), np.full((1, 2), 0.5, np.float32)]
+    i_l2 = [np.array([[0, 1]]), np.array([[2, 3]])]
+    assert merge_shard_lists(s, i_l2, nv.METRIC_L2)[1].tolist() == [[0, 1]]
+    i_ip = [np.array([[1, 0]]), np.array([[3, 2]])]
+    assert merge_shard_lists(s, i_ip, nv.METRIC_IP)[1].tolist() == [[3, 2]]
