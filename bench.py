@@ -225,7 +225,7 @@ def cpu_arms(x: np.ndarray, q_pool: np.ndarray, k: int, requested: int, target_s
         kind, head = "reference", "faiss_IndexFlatIP"
     except Exception:
         pass
-    return {"value": arms[head]["queries_per_s"], "unit": "queries/s", "cores": cores, "kind": kind, "arm": head,
+    return {"value": arms[head]["queries_per_s"], "unit": "queries/s", "cores": cores, "kind": kind, "arm": head, "host": oracle.cpu_budget(),
             "sample": f"{arms[head]['queries']} of the queries x full {n}-row index, once ({arms[head]['seconds']:.1f} s): {arms[head]['what']}",
             "arms": arms, "_sample": sample, "_I": It, "_D": Dt}
 

@@ -291,87 +291,127 @@ __global__ void km_fill_kernel(const int64_t* assign, int64_t n, int64_t L, int 
 }
 
 // ---- step 5b: centroid sums in point order ---------------------------------------------------------------------------------
-// One warp per (centroid, chunk of 32 x V columns), lane = V consecutive columns (one 16-byte load per row), U member rows
-// in flight per step; every column is still one sequential fp32 chain over the members in point order, which is what makes
-// the centroids bit-identical to faiss's compute_centroids. With cent_old the same pass accumulates
-// sum_members ||x - c_old||^2 in fp64 (the iteration's objective).
-template <bool BF16>
+// One block per centroid, thread = V consecutive columns (one 16-byte slice of every member row). Every column is one sequential
+// fp32 chain over the members in point order — that is what makes the centroids bit-identical to faiss's compute_centroids — so
+// the adds cannot be parallelised; the LOADS can: each thread streams its slice of the member rows through a private
+// shared-memory ring with cp.async (ACC_GROUPS groups of ACC_ROWS rows in flight, ~48 KB per block), the member ids of the
+// next group to issue are fetched one step ahead, and the dependent adds run over rows that have already landed.
+// (The first version kept 16 row loads per lane in registers: ncu showed 41 % of all stall samples on the first use of a loaded
+// row and 9 % on the member-id load in front of it, DRAM at 18 % — profiles/r2_kmeans_accumulate_v1_ncu.txt.)
+// With OBJ the same pass accumulates sum_members ||x - c_old||^2 (fp32 partials per group, summed in fp64: fp64 issue is scarce).
+constexpr int ACC_ROWS = 8;    // rows per cp.async group
+constexpr int ACC_GROUPS = 4;  // groups in flight
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool BF16, bool OBJ>
 __global__ void __launch_bounds__(256) km_accumulate_vec_kernel(const void* x, int d, const int64_t* ids, const int32_t* members,
-                                                                 const int64_t* offsets, const float* cent_old, float* cent_out,
-                                                                 float* hassign, double* obj, int normalize) {
+                                                                const int64_t* offsets, const float* cent_old, float* cent_out,
+                                                                float* hassign, double* obj, int normalize, int k, int* work_counter) {
     constexpr int V = BF16 ? 8 : 4;
-    constexpr int U = 16;  // member rows in flight per lane (16 x 16 B): the row gathers are latency bound
-    const int c = blockIdx.x;
+    extern __shared__ __align__(16) uint4 acc_ring[];  // [ACC_GROUPS * ACC_ROWS][blockDim.x]
+    __shared__ int s_c;
     const int lane = threadIdx.x & 31;
-    const int vec = threadIdx.x;  // index of this lane's 16-byte column group inside a row
+  // persistent blocks: as many as fit the machine, each takes the next centroid off a device counter until none is left
+  // (k blocks of unequal length in more than one wave would leave the SMs idle behind the stragglers)
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_c = atomicAdd(work_counter, 1);
+    __syncthreads();
+    const int c = s_c;
+    if (c >= k) break;
+    const int vec = threadIdx.x;  // index of this thread's 16-byte column group inside a row
     const int col0 = vec * V;
     const bool active = col0 < d;
     const int64_t o0 = offsets[c], o1 = offsets[c + 1];
-    const float cntf = (float)(o1 - o0);
+    const int64_t nmem = o1 - o0;
+    const float cntf = (float)nmem;
     if (threadIdx.x == 0) hassign[c] = cntf;
     const size_t row_vecs = (size_t)d / V;
     const uint4* xv = reinterpret_cast<const uint4*>(x);
+    uint4* my_ring = acc_ring + threadIdx.x;
+    const int stride = blockDim.x;
     float acc[V], cold[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) {
         acc[j] = 0.f;
-        cold[j] = (cent_old && active) ? cent_old[(size_t)c * d + col0 + j] : 0.f;
+        cold[j] = (OBJ && active) ? cent_old[(size_t)c * d + col0 + j] : 0.f;
     }
-    double dsum = 0.0;   // objective: fp32 partial sums over the rows of one step, added up in fp64 (fp64 issue is scarce on
-    float part = 0.f;    // this part: one conversion + one add per step instead of four fp64 operations per element)
-    const bool want_obj = cent_old != nullptr;
-    auto consume = [&](const uint4& raw) {
-        float v[V];
-        if constexpr (BF16) {
-            v[0] = __uint_as_float(raw.x << 16); v[1] = __uint_as_float(raw.x & 0xffff0000u);
-            v[2] = __uint_as_float(raw.y << 16); v[3] = __uint_as_float(raw.y & 0xffff0000u);
-            v[4] = __uint_as_float(raw.z << 16); v[5] = __uint_as_float(raw.z & 0xffff0000u);
-            v[6] = __uint_as_float(raw.w << 16); v[7] = __uint_as_float(raw.w & 0xffff0000u);
-        } else {
-            v[0] = __uint_as_float(raw.x); v[1] = __uint_as_float(raw.y); v[2] = __uint_as_float(raw.z); v[3] = __uint_as_float(raw.w);
+    double dsum = 0.0;
+    const int64_t ngroups = (nmem + ACC_ROWS - 1) / ACC_ROWS;
+    // member id of row (g * ACC_ROWS + lane) of this centroid, for lanes < ACC_ROWS (-1 past the end)
+    auto fetch_ids = [&](int64_t g) -> int64_t {
+        const int64_t o = o0 + g * ACC_ROWS + lane;
+        if (lane >= ACC_ROWS || g >= ngroups || o >= o1) return -1;
+        const int64_t p = members[o];
+        return ids ? ids[p] : p;
+    };
+    auto issue = [&](int64_t g, int64_t my_id) {  // all lanes call it; row ids come from lanes 0..ACC_ROWS-1
+        const int slot0 = (int)(g % ACC_GROUPS) * ACC_ROWS;
+#pragma unroll
+        for (int u = 0; u < ACC_ROWS; ++u) {
+            const int64_t r = __shfl_sync(FULL, my_id, u);
+            if (r >= 0 && active) cp_async16(my_ring + (size_t)(slot0 + u) * stride, xv + (size_t)r * row_vecs + vec);
         }
+        cp_async_commit();
+    };
+    // prologue: ACC_GROUPS groups in flight, ids of the next one in registers
+    for (int g = 0; g < ACC_GROUPS; ++g) issue(g, fetch_ids(g));
+    int64_t next_ids = fetch_ids(ACC_GROUPS);
+    for (int64_t g = 0; g < ngroups; ++g) {
+        cp_async_wait<ACC_GROUPS - 1>();  // group g has landed (the groups behind it may still be in flight)
+        const int slot0 = (int)(g % ACC_GROUPS) * ACC_ROWS;
+        const int nrows = (int)((nmem - g * ACC_ROWS) < ACC_ROWS ? (nmem - g * ACC_ROWS) : ACC_ROWS);
+        float part = 0.f;
+        if (active) {
 #pragma unroll
-        for (int j = 0; j < V; ++j) acc[j] = __fadd_rn(acc[j], v[j]);
-        if (want_obj) {
+            for (int u = 0; u < ACC_ROWS; ++u) {
+                if (u < nrows) {
+                    const uint4 raw = my_ring[(size_t)(slot0 + u) * stride];
+                    float v[V];
+                    if constexpr (BF16) {
+                        v[0] = __uint_as_float(raw.x << 16); v[1] = __uint_as_float(raw.x & 0xffff0000u);
+                        v[2] = __uint_as_float(raw.y << 16); v[3] = __uint_as_float(raw.y & 0xffff0000u);
+                        v[4] = __uint_as_float(raw.z << 16); v[5] = __uint_as_float(raw.z & 0xffff0000u);
+                        v[6] = __uint_as_float(raw.w << 16); v[7] = __uint_as_float(raw.w & 0xffff0000u);
+                    } else {
+                        v[0] = __uint_as_float(raw.x); v[1] = __uint_as_float(raw.y); v[2] = __uint_as_float(raw.z); v[3] = __uint_as_float(raw.w);
+                    }
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-                const float df = v[j] - cold[j];
-                part = fmaf(df, df, part);
+                    for (int j = 0; j < V; ++j) acc[j] = __fadd_rn(acc[j], v[j]);
+                    if constexpr (OBJ) {
+#pragma unroll
+                        for (int j = 0; j < V; ++j) {
+                            const float df = v[j] - cold[j];
+                            part = fmaf(df, df, part);
+                        }
+                    }
+                }
             }
         }
-    };
-    int64_t o = o0;
-    for (; o + U <= o1; o += U) {
-        uint4 raw[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t p = members[o + u];  // warp-uniform address
-            const int64_t r = ids ? ids[p] : p;
-            raw[u] = active ? __ldg(xv + (size_t)r * row_vecs + vec) : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) consume(raw[u]);
-        dsum += (double)part;
-        part = 0.f;
+        if constexpr (OBJ) dsum += (double)part;
+        // refill the slot just consumed with group g + ACC_GROUPS, then fetch the ids of the one after it
+        issue(g + ACC_GROUPS, next_ids);
+        next_ids = fetch_ids(g + ACC_GROUPS + 1);
     }
-    for (; o < o1; ++o) {
-        const int64_t p = members[o];
-        const int64_t r = ids ? ids[p] : p;
-        const uint4 raw = active ? __ldg(xv + (size_t)r * row_vecs + vec) : make_uint4(0, 0, 0, 0);
-        consume(raw);
-    }
-    dsum += (double)part;
+    cp_async_wait<0>();
     if (active) {
         float norm = 1.f;
-        if (normalize && o1 > o0) norm = __fdiv_rn(1.0f, cntf);
+        if (normalize && nmem > 0) norm = __fdiv_rn(1.0f, cntf);
 #pragma unroll
-        for (int j = 0; j < V; ++j) cent_out[(size_t)c * d + col0 + j] = (normalize && o1 > o0) ? __fmul_rn(acc[j], norm) : acc[j];
+        for (int j = 0; j < V; ++j) cent_out[(size_t)c * d + col0 + j] = (normalize && nmem > 0) ? __fmul_rn(acc[j], norm) : acc[j];
     }
-    if (want_obj) {
+    if constexpr (OBJ) {
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) dsum += __shfl_xor_sync(FULL, dsum, off);
         if (lane == 0 && dsum != 0.0) atomicAdd(obj, dsum);
     }
+  }
 }
 
 // generic shapes (row size not a multiple of 16 bytes): thread (c, j) sums column j over the members in point order
@@ -439,32 +479,37 @@ struct DevMt19937 {
     }
 };
 
-constexpr int SPLIT_SMEM_K = 8192;  // cluster sizes are walked from shared memory up to this many centroids
+constexpr int SPLIT_SMEM_K = 4096;  // cluster sizes + draw probabilities are walked from shared memory up to this many centroids
 
 __global__ void __launch_bounds__(256) km_split_kernel(int d, int k, int64_t n, float* hassign, float* centroids) {
     __shared__ uint32_t s_mt[624];
     __shared__ int s_cj;
     __shared__ float s_h[SPLIT_SMEM_K];
+    __shared__ float s_p[SPLIT_SMEM_K];  // p[c] = (float)((h[c] - 1.0) / (float)(n - k)), kept current as sizes change
     int any = 0;
     for (int c = threadIdx.x; c < k; c += blockDim.x) any |= hassign[c] == 0.f;
     if (!__syncthreads_or(any)) return;
     float* h = hassign;
-    if (k <= SPLIT_SMEM_K) {  // the rejection walk reads one size per draw: keep them next to the single drawing thread
-        for (int c = threadIdx.x; c < k; c += blockDim.x) s_h[c] = hassign[c];
+    const double denom = (double)(float)(n - k);
+    const bool in_smem = k <= SPLIT_SMEM_K;
+    if (in_smem) {  // the rejection walk reads one probability per draw: keep them next to the single drawing thread
+        for (int c = threadIdx.x; c < k; c += blockDim.x) {
+            s_h[c] = hassign[c];
+            s_p[c] = (float)(((double)s_h[c] - 1.0) / denom);
+        }
         h = s_h;
     }
     DevMt19937 rng{s_mt, 624};
     if (threadIdx.x == 0) rng.seed(1234u);
     __syncthreads();
     const double EPS = 1 / 1024.;
-    const double denom = (double)(float)(n - k);
     for (int ci = 0; ci < k; ++ci) {
         if (h[ci] != 0.f) continue;  // block-uniform (sizes are only written between barriers)
         if (threadIdx.x == 0) {
             int cj = 0;
             for (;; cj = (cj + 1) % k) {
                 // float p = (hassign[cj] - 1.0) / (float)(n - k);  float r = rng.rand_float();
-                const float p = (float)(((double)h[cj] - 1.0) / denom);
+                const float p = in_smem ? s_p[cj] : (float)(((double)h[cj] - 1.0) / denom);
                 const float r = __fdiv_rn(__uint2float_rn(rng.next()), 4294967296.0f);
                 if (r < p) break;
             }
@@ -483,6 +528,10 @@ __global__ void __launch_bounds__(256) km_split_kernel(int d, int k, int64_t n, 
             const float hv = h[cj] / 2;
             h[ci] = hv;
             h[cj] -= hv;
+            if (in_smem) {
+                s_p[ci] = (float)(((double)h[ci] - 1.0) / denom);
+                s_p[cj] = (float)(((double)h[cj] - 1.0) / denom);
+            }
         }
         __syncthreads();
     }
@@ -652,12 +701,31 @@ int update_centroids(b2_index* idx, const void* x, const int64_t* row_ids, int64
     const bool vec_ok = d % V == 0 && d / V <= 256 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     if (vec_ok) {
         const int threads = (int)round_up(d / V, 32);
-        if (idx->dtype == B2_BF16)
-            km_accumulate_vec_kernel<true><<<(unsigned)k, threads, 0, st>>>(x, d, row_ids, w.members.as<int32_t>(), w.offsets.as<int64_t>(),
-                                                                           cent_old, cent_out, w.hassign.as<float>(), obj, normalize);
-        else
-            km_accumulate_vec_kernel<false><<<(unsigned)k, threads, 0, st>>>(x, d, row_ids, w.members.as<int32_t>(), w.offsets.as<int64_t>(),
-                                                                            cent_old, cent_out, w.hassign.as<float>(), obj, normalize);
+        const size_t ring = (size_t)ACC_GROUPS * ACC_ROWS * threads * sizeof(uint4);
+        const bool want_obj = cent_old != nullptr;
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, idx->device);
+        B2_TRY(w.scalar.ensure(64));
+        int* counter = reinterpret_cast<int*>(w.scalar.as<char>() + 48);
+        B2_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+#define B2_ACC_LAUNCH(BF, OB)                                                                                                     \
+    do {                                                                                                                          \
+        auto kern = km_accumulate_vec_kernel<BF, OB>;                                                                             \
+        if (ring > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));        \
+        int per_sm = 1;                                                                                                           \
+        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, ring));                                     \
+        const int grid = (int)std::min<int64_t>(k, (int64_t)std::max(per_sm, 1) * sms);                                           \
+        kern<<<grid, threads, ring, st>>>(x, d, row_ids, w.members.as<int32_t>(), w.offsets.as<int64_t>(), cent_old, cent_out,    \
+                                          w.hassign.as<float>(), obj, normalize, k, counter);                                     \
+    } while (0)
+        if (idx->dtype == B2_BF16) {
+            if (want_obj) B2_ACC_LAUNCH(true, true);
+            else B2_ACC_LAUNCH(true, false);
+        } else {
+            if (want_obj) B2_ACC_LAUNCH(false, true);
+            else B2_ACC_LAUNCH(false, false);
+        }
+#undef B2_ACC_LAUNCH
     } else {
         dim3 grid((unsigned)k, (unsigned)ceil_div(d, 128));
         km_accumulate_kernel<<<grid, 128, 0, st>>>(x, idx->dtype, d, row_ids, w.members.as<int32_t>(), w.offsets.as<int64_t>(), cent_old,

@@ -155,12 +155,7 @@ def num_threads() -> int:
 
 def use_all_cores() -> int:
     """Give OpenMP every core this process may run on, whatever OMP_NUM_THREADS said (torchrun sets it to 1)."""
-    import os
-    try:
-        n = len(os.sched_getaffinity(0))
-    except AttributeError:  # pragma: no cover
-        n = os.cpu_count() or 1
-    lib().orc_set_num_threads(n)
+    lib().orc_set_num_threads(cpu_budget()["threads"])
     return num_threads()
 
 
@@ -281,11 +276,40 @@ def knn_sgemm(x, q, k, metric=IP, q_block: int = 2048, x_block: int = 65536):
     return D, I
 
 
-def use_all_cores_native() -> int:
+def cpu_budget() -> dict:
+    """Host cores this process may really use: the affinity mask, capped by the cgroup CPU quota when the container has one
+    (a container that SEES 128 cores but is allowed 16 CPU-seconds per second only thrashes with 128 threads)."""
     try:
-        n = len(os.sched_getaffinity(0))
+        aff = len(os.sched_getaffinity(0))
     except AttributeError:  # pragma: no cover
-        n = os.cpu_count() or 1
+        aff = os.cpu_count() or 1
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            q, per = f.read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:
+                q = float(f.read())
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+                per = float(f.read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            quota = None
+    use = aff if quota is None else max(1, min(aff, int(quota + 0.5)))
+    load = None
+    try:
+        load = os.getloadavg()[0]
+    except Exception:
+        pass
+    return {"affinity": aff, "cgroup_quota_cpus": quota, "threads": use, "loadavg_1m": load}
+
+
+def use_all_cores_native() -> int:
+    n = cpu_budget()["threads"]
     native_lib().orc_set_num_threads(n)
     return int(native_lib().orc_num_threads())
 

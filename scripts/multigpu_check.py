@@ -39,7 +39,15 @@ def main():
         s, i = sh.search(torch.from_numpy(q).to(dev), 10, ids=ids)
         Ds, Is = oracle.knn_subset(x, q, 10, ids, metric)
         good &= np.array_equal(i.cpu().numpy(), Is) and np.array_equal(s.cpu().numpy().view(np.uint32), Ds.view(np.uint32))
-        print(f"[rank {rank}] sharded search metric={metric}: {'OK' if good else 'MISMATCH'}", flush=True)
+        # the end-to-end form: every rank copies 1/world of the pinned host queries, slices all-gathered over NVLink
+        qh = torch.from_numpy(q).pin_memory()
+        s2, i2 = sh.search_host(qh, 10)
+        good &= np.array_equal(i2.cpu().numpy(), Io) and np.array_equal(s2.cpu().numpy().view(np.uint32), Do.view(np.uint32))
+        # a large k through the packed exchange (8 ranks x 128 = the merge kernel's 1024-candidate limit)
+        s3, i3 = sh.search(torch.from_numpy(q[:50]).to(dev), 100)
+        D3, I3 = oracle.knn(x, q[:50], 100, metric)
+        good &= np.array_equal(i3.cpu().numpy(), I3) and np.array_equal(s3.cpu().numpy().view(np.uint32), D3.view(np.uint32))
+        print(f"[rank {rank}] sharded search metric={metric} (device, host-buffer and k=100 forms): {'OK' if good else 'MISMATCH'}", flush=True)
         ok &= good
         sh.close()
 
