@@ -711,7 +711,7 @@ int update_centroids(b2_index* idx, const void* x, const int64_t* row_ids, int64
 #define B2_ACC_LAUNCH(BF, OB)                                                                                                     \
     do {                                                                                                                          \
         auto kern = km_accumulate_vec_kernel<BF, OB>;                                                                             \
-        if (ring > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));        \
+        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring)); /* ring + static > 48 KB */  \
         int per_sm = 1;                                                                                                           \
         B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, ring));                                     \
         const int grid = (int)std::min<int64_t>(k, (int64_t)std::max(per_sm, 1) * sms);                                           \
