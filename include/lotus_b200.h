@@ -123,6 +123,17 @@ B2_API int b2_index_search_packed_dev(b2_index* idx, const void* q_dev, int64_t 
 B2_API int b2_merge_topk_packed_dev(const uint64_t* packed_dev, const int64_t* shard_offsets, int32_t g, int64_t nq, int32_t k,
                              int32_t metric, int32_t device, float* out_scores_dev, int64_t* out_idx_dev, void* stream);
 
+/* Row-sharded search in two stages, so that the ranks can tell each other how good the merged top k will be BEFORE the exact
+ * re-scoring. Stage 1 filters this shard (tcgen05 kernel) and writes lower_dev[nq]: for every query a lower bound on the exact
+ * score of its j best local candidates (-inf when unknown); it only enqueues work on `stream`. The caller all-reduces (MIN)
+ * lower_dev over the ranks with j = ceil(k / ranks) — k rows of the whole index are then known to reach that score — and hands
+ * the result to stage 2, which re-scores only the local candidates that can still reach it (about k / ranks instead of k + 2),
+ * certifies against it, and writes the packed [nq,k] list like b2_index_search_packed_dev. q_dev must stay valid until
+ * stage 2 returns. One staged search in flight per handle. */
+B2_API int b2_index_search_stage1_dev(b2_index* idx, const void* q_dev, int64_t nq, int32_t q_dtype, int32_t k, int32_t j,
+                               float* lower_dev, void* stream);
+B2_API int b2_index_search_stage2_packed_dev(b2_index* idx, const float* hint_dev, uint64_t* out_packed_dev, void* stream);
+
 /* ---- row gather (faiss_vs.py:38-41) ------------------------------------------------------------------ */
 /* out[m,d] in the index's dtype = x[ids]; HOST out unless out_on_device != 0 (then ids is a device pointer too) */
 B2_API int b2_index_gather(b2_index* idx, const int64_t* ids, int64_t m, void* out, int32_t out_on_device);

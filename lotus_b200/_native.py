@@ -19,7 +19,7 @@ OK, EINVAL, ENODEV, ECUDA, ENOMEM, ERANGE = 0, -1, -2, -3, -4, -5
 SYMBOLS = [
     "b2_abi_version", "b2_last_error", "b2_device_count", "b2_max_k", "b2_index_create", "b2_index_free",
     "b2_index_ntotal", "b2_index_dim", "b2_index_dtype", "b2_index_metric", "b2_index_device", "b2_index_data_dev",
-    "b2_index_search", "b2_index_search_dev", "b2_merge_topk_dev", "b2_index_search_packed_dev", "b2_merge_topk_packed_dev", "b2_index_gather", "b2_threshold_pairs",
+    "b2_index_search", "b2_index_search_dev", "b2_merge_topk_dev", "b2_index_search_packed_dev", "b2_merge_topk_packed_dev", "b2_index_search_stage1_dev", "b2_index_search_stage2_packed_dev", "b2_index_gather", "b2_threshold_pairs",
     "b2_connected_components", "b2_kmeans", "b2_kmeans_assign", "b2_kmeans_accumulate", "b2_kmeans_assign_dev", "b2_kmeans_accumulate_dev", "b2_stats", "b2_stats_reset", "b2_last_filter_ms", "b2_host_f32_to_bf16",
 ]
 
@@ -68,6 +68,10 @@ def lib() -> ctypes.CDLL:
     L.b2_index_search_packed_dev.argtypes = [vp, vp, i64, i32, i32, vp, vp]
     L.b2_merge_topk_packed_dev.restype = c.c_int
     L.b2_merge_topk_packed_dev.argtypes = [vp, vp, i32, i64, i32, i32, i32, vp, vp, vp]
+    L.b2_index_search_stage1_dev.restype = c.c_int
+    L.b2_index_search_stage1_dev.argtypes = [vp, vp, i64, i32, i32, i32, vp, vp]
+    L.b2_index_search_stage2_packed_dev.restype = c.c_int
+    L.b2_index_search_stage2_packed_dev.argtypes = [vp, vp, vp, vp]
     L.b2_index_gather.restype = c.c_int
     L.b2_index_gather.argtypes = [vp, vp, i64, vp, i32]
     L.b2_threshold_pairs.restype = c.c_int
@@ -209,6 +213,14 @@ class Index:
         """Whole-index search, result as one uint64 per entry (float32 score bits << 32 | local row id, 0xffffffff = none)."""
         check(lib().b2_index_search_packed_dev(self._h, ctypes.c_void_p(q_ptr), nq, q_dtype, k, ctypes.c_void_p(out_packed_ptr),
                                                ctypes.c_void_p(stream) if stream else None))
+
+    def search_stage1_dev(self, q_ptr: int, nq: int, k: int, q_dtype: int, j: int, lower_ptr: int, stream: int = 0) -> None:
+        check(lib().b2_index_search_stage1_dev(self._h, ctypes.c_void_p(q_ptr), nq, q_dtype, k, j, ctypes.c_void_p(lower_ptr),
+                                               ctypes.c_void_p(stream) if stream else None))
+
+    def search_stage2_packed_dev(self, hint_ptr: int, out_packed_ptr: int, stream: int = 0) -> None:
+        check(lib().b2_index_search_stage2_packed_dev(self._h, ctypes.c_void_p(hint_ptr), ctypes.c_void_p(out_packed_ptr),
+                                                      ctypes.c_void_p(stream) if stream else None))
 
     def gather(self, ids) -> np.ndarray:
         ids = np.ascontiguousarray(ids, dtype=np.int64)

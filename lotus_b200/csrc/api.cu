@@ -338,7 +338,7 @@ int b2_index_create(const void* x, int64_t n, int32_t d, int32_t dtype, int32_t 
 void b2_index_free(b2_index* idx) {
     if (!idx) return;
     DeviceGuard guard(idx->device);
-    DevBuf* bufs[] = {&idx->store, &idx->filt_pad, &idx->filt16, &idx->sub_filt16, &idx->defer, &idx->q_sub, &idx->sub_sc, &idx->sub_id, &idx->norm2, &idx->scalar, &idx->q_in, &idx->q_filt, &idx->cand_score,
+    DevBuf* bufs[] = {&idx->store, &idx->filt_pad, &idx->filt16, &idx->sub_filt16, &idx->defer, &idx->q_sub, &idx->sub_sc, &idx->sub_id, &idx->q_norm2, &idx->norm2, &idx->scalar, &idx->q_in, &idx->q_filt, &idx->cand_score,
                       &idx->cand_id, &idx->cand_thr, &idx->flags, &idx->sel, &idx->dense, &idx->out_sc, &idx->out_id,
                       &idx->ids_dev, &idx->sub_store, &idx->sub_filt, &idx->sub_norm2, &idx->sort_keys};
     for (DevBuf* b : bufs) b->release();
@@ -448,6 +448,112 @@ int b2_index_search_packed_dev(b2_index* idx, const void* q_dev, int64_t nq, int
     B2_TRY(idx->out_sc.ensure((size_t)nq * k * sizeof(float)));
     B2_TRY(idx->out_id.ensure((size_t)nq * k * sizeof(int64_t)));
     B2_TRY(search_core(idx, idx->view, idx->metric, q_dev, q_dtype, nq, k, nullptr, 0, idx->out_sc.as<float>(), idx->out_id.as<int64_t>(), st));
+    B2_TRY(launch_pack_topk(idx->out_sc.as<float>(), idx->out_id.as<int64_t>(), nq * (int64_t)k, out_packed_dev, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    return B2_OK;
+}
+
+// ---- row-sharded search in two stages ---------------------------------------------------------------------------------------
+// stage 1: filter this shard, report per query a lower bound on the exact score of its j best local candidates (asynchronous:
+// nothing is copied to the host). The caller all-reduces (MIN) the bounds over the ranks with j = ceil(k / ranks): k rows of the
+// whole index are then known to reach that score. stage 2: finalize with that bound as a hint — rows that cannot reach it are
+// not re-scored and the certificate only has to beat the hint — and pack. Shapes the staged path does not cover (dense path,
+// fp32 two-level search, more than one query chunk, too many candidate entries) report -inf bounds and stage 2 runs the plain
+// search, so the pair of calls is always valid.
+int b2_index_search_stage1_dev(b2_index* idx, const void* q_dev, int64_t nq, int32_t q_dtype, int32_t k, int32_t j, float* lower_dev,
+                               void* stream) {
+    B2_TRY(check_search_args(idx, q_dev, nq, q_dtype, k));
+    if (nq == 0) return B2_OK;
+    if (!lower_dev || j <= 0) { set_error("bad stage-1 arguments"); return B2_EINVAL; }
+    DeviceGuard guard(idx->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    b2_index::Staged& sg = idx->staged;
+    sg = b2_index::Staged();
+    sg.active = true;
+    sg.q = q_dev;
+    sg.nq = nq;
+    sg.q_dtype = q_dtype;
+    sg.k = k;
+    const MatView& X = idx->view;
+    const int kp = filter_kp_for_k(k);
+    const int min_splits = filter_min_splits_for_k(k);
+    const bool use_filter = kp != 0 && X.n >= 512 && ceil_div(X.n, 256) >= min_splits && X.n >= 4 * (int64_t)k;
+    const bool two_level = X.filt16 != nullptr && k <= 24 && X.n >= 4096;
+    const int64_t chunk = std::max<int64_t>(4096, std::min<int64_t>(1 << 20, (4LL << 30) / ((int64_t)std::max(min_splits, 8) * kp * 8)));
+    int dev_sms = 148;
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, idx->device);
+    const bool two_cta = filter_use_pair(nq);
+    const int n_splits = use_filter ? filter_choose_splits(nq, X.n, dev_sms, two_cta, false, min_splits) : 0;
+    if (!use_filter || two_level || nq > chunk || n_splits <= 0 || 2 * n_splits * (kp / 2) > shard_lower_bound_max_entries() || j > k) {
+        return launch_fill_f32(lower_dev, nq, -INFINITY, st);  // stage 2 will run the plain search
+    }
+    idx->last_filter_ms = -1.f;
+    const int filt_dtype = X.filt_dtype;
+    const int64_t q_pitch = round_up(X.d, filt_dtype == B2_F32 ? 4 : 8);
+    const bool q_in_place = q_dtype == filt_dtype && q_pitch == X.d && (reinterpret_cast<uintptr_t>(q_dev) & 15) == 0;
+    if (!q_in_place) {
+        B2_TRY(idx->q_filt.ensure((size_t)nq * q_pitch * esize(filt_dtype)));
+        B2_TRY(launch_prep_queries(q_dev, q_dtype, nq, X.d, idx->q_filt.p, filt_dtype, q_pitch, st));
+    }
+    const void* q_filt = q_in_place ? q_dev : idx->q_filt.p;
+    B2_TRY(idx->cand_score.ensure((size_t)nq * n_splits * kp * sizeof(float)));
+    B2_TRY(idx->cand_id.ensure((size_t)nq * n_splits * kp * sizeof(int32_t)));
+    B2_TRY(idx->cand_thr.ensure((size_t)nq * n_splits * 2 * sizeof(float)));
+    B2_TRY(idx->q_norm2.ensure((size_t)nq * sizeof(float)));
+    B2_TRY(idx->scalar.ensure(64));
+    B2_CUDA(cudaEventRecord(idx->ev0, st));
+    B2_TRY(launch_knn_filter(X, q_filt, q_pitch, nq, idx->metric, kp, n_splits, two_cta, idx->cand_score.as<float>(), idx->cand_id.as<int32_t>(),
+                             idx->cand_thr.as<float>(), idx->device, st));
+    B2_CUDA(cudaEventRecord(idx->ev1, st));
+    sg.kp = kp;
+    sg.n_splits = n_splits;
+    sg.rel_eps = filter_rel_eps(X.dtype, filt_dtype, q_dtype, X.d);
+    sg.filtered = true;
+    B2_TRY(launch_row_norms(q_dev, q_dtype, nq, X.d, idx->q_norm2.as<float>(), idx->scalar.as<float>() + 8, st));
+    B2_TRY(launch_shard_lower_bound(idx->cand_score.as<float>(), idx->cand_id.as<int32_t>(), nq, 2 * n_splits, kp / 2, j, idx->q_norm2.as<float>(),
+                                    X.max_norm, sg.rel_eps, idx->metric, lower_dev, st));
+    g_stats[ST_QUERIES] += nq;
+    return B2_OK;
+}
+
+int b2_index_search_stage2_packed_dev(b2_index* idx, const float* hint_dev, uint64_t* out_packed_dev, void* stream) {
+    if (!idx) { set_error("Index not loaded"); return B2_EINVAL; }
+    b2_index::Staged sg = idx->staged;
+    idx->staged.active = false;
+    if (!sg.active) { set_error("stage 2 without a stage 1"); return B2_EINVAL; }
+    if (!out_packed_dev) { set_error("output buffer is NULL"); return B2_EINVAL; }
+    if (!sg.filtered) return b2_index_search_packed_dev(idx, sg.q, sg.nq, sg.q_dtype, sg.k, out_packed_dev, stream);
+    if (idx->n > 0xfffffffeLL) { set_error("packed lists hold 32-bit local ids"); return B2_ERANGE; }
+    DeviceGuard guard(idx->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const MatView& X = idx->view;
+    const int64_t nq = sg.nq;
+    const int k = sg.k;
+    B2_TRY(idx->out_sc.ensure((size_t)nq * k * sizeof(float)));
+    B2_TRY(idx->out_id.ensure((size_t)nq * k * sizeof(int64_t)));
+    B2_TRY(idx->flags.ensure((size_t)nq * sizeof(int32_t)));
+    B2_TRY(idx->sel.ensure((size_t)(nq + 1) * sizeof(int32_t)));
+    B2_TRY(idx->h_flags.ensure(64));
+    int32_t* sel_count = idx->sel.as<int32_t>();
+    int32_t* sel_list = sel_count + 1;
+    B2_CUDA(cudaMemsetAsync(sel_count, 0, sizeof(int32_t), st));
+    B2_TRY(launch_finalize(X, sg.q, sg.q_dtype, nq, idx->metric, k, sg.kp, sg.kp / 2, 2 * sg.n_splits, idx->cand_score.as<float>(),
+                           idx->cand_id.as<int32_t>(), idx->cand_thr.as<float>(), sg.rel_eps, nullptr, 0, idx->out_sc.as<float>(),
+                           idx->out_id.as<int64_t>(), idx->flags.as<int32_t>(), sel_list, sel_count, st, hint_dev));
+    int32_t* h_count = reinterpret_cast<int32_t*>(idx->h_flags.p);
+    B2_CUDA(cudaMemcpyAsync(h_count, sel_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    cudaError_t se = cudaStreamSynchronize(st);
+    if (se != cudaSuccess) { set_error("search pipeline failed on the device: %s", cudaGetErrorString(se)); return B2_ECUDA; }
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, idx->ev0, idx->ev1) == cudaSuccess) idx->last_filter_ms = ms;
+    const int64_t n_sel = *h_count;
+    if (n_sel > 0) {  // uncertified queries: the exact local top-k (a superset of what the merge needs)
+        g_stats[ST_FALLBACK] += n_sel;
+        const int64_t rows = std::min<int64_t>(std::max<int64_t>(1, (int64_t)(512ull << 20) / (std::max<int64_t>(X.n, 1) * 4)), n_sel);
+        B2_TRY(idx->dense.ensure((size_t)rows * X.n * sizeof(float)));
+        B2_TRY(launch_dense_topk(X, sg.q, sg.q_dtype, nq, sel_list, n_sel, idx->metric, k, nullptr, 0, idx->dense.as<float>(), rows, nullptr,
+                                 idx->out_sc.as<float>(), idx->out_id.as<int64_t>(), st));
+    }
     B2_TRY(launch_pack_topk(idx->out_sc.as<float>(), idx->out_id.as<int64_t>(), nq * (int64_t)k, out_packed_dev, st));
     B2_CUDA(cudaStreamSynchronize(st));
     return B2_OK;

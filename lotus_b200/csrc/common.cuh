@@ -128,7 +128,11 @@ int launch_gather_rows(const void* x, int dtype, int d, const int64_t* ids, int6
 int launch_finalize(const MatView& X, const void* q, int q_dtype, int64_t nq, int metric, int k, int kp, int list_len,
                     int n_lists, const float* cand_score, const int32_t* cand_id, const float* cand_thr,
                     float rel_eps, const int64_t* id_map, int64_t id_offset, float* out_scores, int64_t* out_idx,
-                    int32_t* flags, int32_t* sel, int32_t* sel_count, cudaStream_t stream);
+                    int32_t* flags, int32_t* sel, int32_t* sel_count, cudaStream_t stream, const float* hint = nullptr);
+int shard_lower_bound_max_entries();
+int launch_shard_lower_bound(const float* cand_score, const int32_t* cand_id, int64_t nq, int n_lists, int list_len, int j, const float* qnorm2,
+                             float max_norm, float rel_eps, int metric, float* lower, cudaStream_t stream);
+int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t stream);
 int launch_dense_topk(const MatView& X, const void* q, int q_dtype, int64_t nq, const int32_t* q_sel,
                       int64_t n_sel, int metric, int k, const int64_t* id_map, int64_t id_offset, float* dense_ws,
                       int64_t dense_ws_rows, uint64_t* sort_ws, float* out_scores, int64_t* out_idx, cudaStream_t stream);

@@ -95,6 +95,15 @@ struct b2_index {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_filter_ms = -1.f;
     b2::KmWork* km = nullptr;
+    // row-sharded search in two stages (b2_index_search_stage1_dev / _stage2_packed_dev): what stage 1 left for stage 2
+    struct Staged {
+        bool active = false, filtered = false;  // filtered: the candidate lists of (q, nq, k) are in the workspace
+        const void* q = nullptr;
+        int64_t nq = 0;
+        int32_t q_dtype = 0, k = 0, kp = 0, n_splits = 0;
+        float rel_eps = 0.f;
+    } staged;
+    DevBuf q_norm2;
 };
 
 namespace b2 {

@@ -257,6 +257,8 @@ struct FinalizeParams {
     int32_t list_len;                                    // entries per candidate list (<= 32*R)
     float rel_eps, max_norm;
     const float* max_norm_dev;  // nullable: overrides max_norm
+    const float* hint;          // nullable: per query, a lower bound (filter-score space) on the k-th exact score of the WHOLE
+                                // row-sharded search (b2_index_search_stage1_dev + all-reduce MIN over the ranks)
 };
 
 constexpr int FIN_WARPS = 4;
@@ -343,6 +345,12 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(const Finalize
         const float tk = s_ex[p.k - 1];
         if (tk > -INFINITY) cut = (float)((double)tk - 2.0 * eps_f - 4.8e-7 * fabs((double)tk));
     }
+    // Row-sharded search: k rows with exact score >= hint exist somewhere in the index, so a local row whose exact score is surely
+    // below that (filter + eps < hint) cannot enter or tie the merged top k: do not re-score it (this is what lets 8 ranks
+    // re-score ~k/8 rows each instead of k+2).
+    const double hint = p.hint ? (double)p.hint[q] : -INFINITY;
+    const double hint_slack = 4.8e-7 * fabs(hint) + (is_l2 ? 4.8e-7 * qn2 : 0.0);
+    if (hint > -INFINITY) cut = fmaxf(cut, (float)(hint - eps_f - hint_slack));
     __syncwarp();
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -461,7 +469,9 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(const Finalize
 
     // 6. certification against everything the filter discarded
     bool certified = true;
-    if (bound > -INFINITY) {
+    // everything the filter discarded scores (exactly) at most bound + eps: below the sharded search's k-th score -> irrelevant
+    const bool hint_ok = hint > -INFINITY && ((double)bound + eps_f) < hint - hint_slack;
+    if (bound > -INFINITY && !hint_ok) {
         if (nvalid < k) {
             certified = false;  // cannot happen (lists only overflow when full); be safe
         } else {
@@ -804,6 +814,64 @@ __global__ void exact_l2_assigned_kernel(const void* pts, int dtype, int64_t m, 
     }
 }
 
+// Row-sharded search, stage 1: lower[q] = (the j-th best filter score among this shard's candidates) - eps, a lower bound on the
+// exact scores of j rows of this shard. After an all-reduce(MIN) over the ranks with j = ceil(k / ranks), ranks * j >= k rows of
+// the index are known to score at least that much. Warp per query; up to 32 * LB_R candidate entries.
+constexpr int LB_R = 16;
+__global__ void shard_lower_bound_kernel(const float* cand_score, const int32_t* cand_id, int64_t nq, int n_lists, int list_len, int j,
+                                         const float* qnorm2, float max_norm, float rel_eps, int metric, float* lower) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (q >= nq) return;
+    const int total = n_lists * list_len;
+    float v[LB_R];
+#pragma unroll
+    for (int r = 0; r < LB_R; ++r) {
+        const int e = r * 32 + lane;
+        float s = -INFINITY;
+        if (e < total) {
+            const size_t off = (size_t)q * total + e;
+            if (cand_id[off] >= 0) s = cand_score[off];
+        }
+        v[r] = s;
+    }
+    float tj = -INFINITY;
+    for (int t = 0; t < j; ++t) {
+        float m = v[0];
+#pragma unroll
+        for (int r = 1; r < LB_R; ++r) m = fmaxf(m, v[r]);
+        float M = m;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) M = fmaxf(M, __shfl_xor_sync(FULL, M, off));
+        tj = M;
+        if (!(M > -INFINITY)) break;  // fewer than j candidates (or NaN): no bound
+        const unsigned owners = __ballot_sync(FULL, m == M);
+        if (lane == __ffs(owners) - 1) {  // remove ONE instance of the maximum
+            bool done = false;
+#pragma unroll
+            for (int r = 0; r < LB_R; ++r)
+                if (!done && v[r] == M) {
+                    v[r] = -INFINITY;
+                    done = true;
+                }
+        }
+    }
+    if (lane == 0) {
+        float out = -INFINITY;
+        if (tj > -INFINITY) {
+            const double qn = sqrt((double)qnorm2[q]), mx = (double)max_norm;
+            const double eps = metric == B2_METRIC_L2 ? 2.0 * (double)rel_eps * qn * mx + 2.4e-7 * (mx * mx + 2.0 * qn * mx) + 1.3e-7 * qn * qn + 1e-30
+                                                      : (double)rel_eps * qn * mx * (1.0 + 1.3e-7) + 1e-30;
+            out = (float)((double)tj - eps - 4.8e-7 * fabs((double)tj));
+        }
+        lower[q] = out;
+    }
+}
+
+__global__ void fill_f32_kernel(float* p, int64_t n, float v) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) p[t] = v;
+}
+
 int grid_for(int64_t work_items, int threads, int cap = 148 * 16) {
     int64_t g = ceil_div(work_items, threads);
     if (g < 1) g = 1;
@@ -827,6 +895,24 @@ int launch_row_norms(const void* x, int dtype, int64_t n, int d, float* norm2, f
     B2_CUDA(cudaMemsetAsync(max_norm_dev, 0, sizeof(float), stream));
     if (n <= 0) return B2_OK;
     row_norms_kernel<<<grid_for(n * 32, 256), 256, 0, stream>>>(x, dtype, n, d, norm2, max_norm_dev);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+int shard_lower_bound_max_entries() { return 32 * LB_R; }
+
+int launch_shard_lower_bound(const float* cand_score, const int32_t* cand_id, int64_t nq, int n_lists, int list_len, int j, const float* qnorm2,
+                             float max_norm, float rel_eps, int metric, float* lower, cudaStream_t stream) {
+    if (nq <= 0) return B2_OK;
+    shard_lower_bound_kernel<<<(unsigned)ceil_div(nq * 32, 128), 128, 0, stream>>>(cand_score, cand_id, nq, n_lists, list_len, j, qnorm2, max_norm,
+                                                                                  rel_eps, metric, lower);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t stream) {
+    if (n <= 0) return B2_OK;
+    fill_f32_kernel<<<grid_for(n, 256), 256, 0, stream>>>(p, n, v);
     B2_LAUNCH_CHECK();
     return B2_OK;
 }
@@ -884,9 +970,10 @@ static int launch_finalize_r(const FinalizeParams& p, cudaStream_t stream) {
 int launch_finalize(const MatView& X, const void* q, int q_dtype, int64_t nq, int metric, int k, int kp, int list_len,
                     int n_splits, const float* cand_score, const int32_t* cand_id, const float* cand_thr,
                     float rel_eps, const int64_t* id_map, int64_t id_offset, float* out_scores, int64_t* out_idx,
-                    int32_t* flags, int32_t* sel, int32_t* sel_count, cudaStream_t stream) {
+                    int32_t* flags, int32_t* sel, int32_t* sel_count, cudaStream_t stream, const float* hint) {
     if (nq <= 0) return B2_OK;
     FinalizeParams p;
+    p.hint = hint;
     p.sel = sel;
     p.sel_count = sel_count;
     p.store = X.store;

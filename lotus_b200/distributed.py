@@ -104,7 +104,15 @@ class ShardedIndex:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()
         loc = torch.empty((nq, k), dtype=torch.int64, device=q.device)  # uint64 words (torch has no uint64 collectives)
-        self.index.search_packed_dev(q.data_ptr(), nq, k, q_dtype, loc.data_ptr(), stream=stream)
+        if os.environ.get("B2_SHARD_STAGED", "1") != "0":
+            # two stages: filter, tell the other ranks how good this shard's best ceil(k/G) candidates are (one all-reduce MIN of
+            # nq floats), then re-score only what can still reach the merged top k
+            lower = torch.empty(nq, dtype=torch.float32, device=q.device)
+            self.index.search_stage1_dev(q.data_ptr(), nq, k, q_dtype, -(-k // self.world), lower.data_ptr(), stream=stream)
+            self.dist.all_reduce(lower, op=self.dist.ReduceOp.MIN, group=self.group)
+            self.index.search_stage2_packed_dev(lower.data_ptr(), loc.data_ptr(), stream=stream)
+        else:
+            self.index.search_packed_dev(q.data_ptr(), nq, k, q_dtype, loc.data_ptr(), stream=stream)
         if timing:
             ev[1].record()
         allp = torch.empty((self.world, nq, k), dtype=torch.int64, device=q.device)
