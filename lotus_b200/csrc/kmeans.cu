@@ -32,11 +32,11 @@ namespace b2 {
 
 struct KmWork {
     DevBuf cent[2], cent_filt, cent_norm2, scalar, pts, pts_norm2, train, train_norm2, assign, members, offsets, totals, blk, hassign, ids,
-        obj, flag_ids, flag_count, hard_ids, sub, sub_dis, sub_assign, fin_assign, fin_dis, perm;
+        obj, flag_ids, flag_count, hard_ids, order, sub, sub_dis, sub_assign, fin_assign, fin_dis, perm;
     HostBuf h_count;
     void release() {
         DevBuf* all[] = {&cent[0], &cent[1], &cent_filt, &cent_norm2, &scalar, &pts, &pts_norm2, &train, &train_norm2, &assign, &members,
-                         &offsets, &totals, &blk, &hassign, &ids, &obj, &flag_ids, &flag_count, &hard_ids, &sub, &sub_dis, &sub_assign, &fin_assign,
+                         &offsets, &totals, &blk, &hassign, &ids, &obj, &flag_ids, &flag_count, &hard_ids, &order, &sub, &sub_dis, &sub_assign, &fin_assign,
                          &fin_dis, &perm};
         for (DevBuf* b : all) b->release();
         h_count.release();
@@ -291,16 +291,22 @@ __global__ void km_fill_kernel(const int64_t* assign, int64_t n, int64_t L, int 
 }
 
 // ---- step 5b: centroid sums in point order ---------------------------------------------------------------------------------
-// One block per centroid, thread = V consecutive columns (one 16-byte slice of every member row). Every column is one sequential
-// fp32 chain over the members in point order — that is what makes the centroids bit-identical to faiss's compute_centroids — so
-// the adds cannot be parallelised; the LOADS can: each thread streams its slice of the member rows through a private
-// shared-memory ring with cp.async (ACC_GROUPS groups of ACC_ROWS rows in flight, ~48 KB per block), the member ids of the
-// next group to issue are fetched one step ahead, and the dependent adds run over rows that have already landed.
-// (The first version kept 16 row loads per lane in registers: ncu showed 41 % of all stall samples on the first use of a loaded
-// row and 9 % on the member-id load in front of it, DRAM at 18 % — profiles/r2_kmeans_accumulate_v1_ncu.txt.)
+// Every column of a centroid is ONE sequential fp32 chain over its members in point order — that is what makes the centroids
+// bit-identical to faiss's compute_centroids — so the adds of a chain cannot be parallelised. What can:
+//   * different centroids and different COLUMN chunks are independent: a work item is (centroid, chunk of 32 x V columns),
+//     handled by one warp (lane = V consecutive columns = one 16-byte slice of every member row);
+//   * the LOADS of a chain: each warp streams its slice of the member rows through a private shared-memory ring with cp.async
+//     (ACC_GROUPS x ACC_ROWS = 32 rows in flight, member ids fetched two groups ahead), the dependent adds run over rows that
+//     have already landed;
+//   * balance: cluster sizes are far from equal while Lloyd is converging (some centroids hold 4x the mean), and the longest
+//     chain bounds the pass — warps pull items off a device counter in DECREASING cluster size (km_order_kernel).
+// History (profiles/r2_kmeans_accumulate_*): v1, one block per centroid with 16 row loads per lane in registers: 5.2 ms at
+// 5M x 768, DRAM 18 %, SMs active 29 % of the time (tail of the largest clusters), 41 % of stall samples on the first use of a
+// loaded row; v2, the same shape with a cp.async ring: no better (6.6 ms) — the per-centroid chain, not the load depth, was the bound.
 // With OBJ the same pass accumulates sum_members ||x - c_old||^2 (fp32 partials per group, summed in fp64: fp64 issue is scarce).
 constexpr int ACC_ROWS = 8;    // rows per cp.async group
 constexpr int ACC_GROUPS = 4;  // groups in flight
+constexpr int ACC_WARPS = 4;   // warps per block (each with its own 16 KB ring)
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -309,109 +315,129 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// order[i] = centroid ids by decreasing size class (floor(log2(size)); exact order inside a class does not matter): one block
+__global__ void km_order_kernel(const int32_t* totals, int k, int32_t* order) {
+    __shared__ int s_cnt[33], s_base[33];
+    if (threadIdx.x < 33) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (int c = threadIdx.x; c < k; c += blockDim.x) atomicAdd(&s_cnt[32 - __clz(max(totals[c], 0))], 1);  // class 0: empty
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int cls = 32; cls >= 0; --cls) {
+            s_base[cls] = run;
+            run += s_cnt[cls];
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < k; c += blockDim.x) order[atomicAdd(&s_base[32 - __clz(max(totals[c], 0))], 1)] = c;
+}
+
 template <bool BF16, bool OBJ>
-__global__ void __launch_bounds__(256) km_accumulate_vec_kernel(const void* x, int d, const int64_t* ids, const int32_t* members,
-                                                                const int64_t* offsets, const float* cent_old, float* cent_out,
-                                                                float* hassign, double* obj, int normalize, int k, int* work_counter) {
+__global__ void __launch_bounds__(ACC_WARPS * 32) km_accumulate_vec_kernel(const void* x, int d, const int64_t* ids, const int32_t* members,
+                                                                           const int64_t* offsets, const int32_t* order, const float* cent_old,
+                                                                           float* cent_out, float* hassign, double* obj, int normalize, int k,
+                                                                           int n_chunks, int* work_counter) {
     constexpr int V = BF16 ? 8 : 4;
-    extern __shared__ __align__(16) uint4 acc_ring[];  // [ACC_GROUPS * ACC_ROWS][blockDim.x]
-    __shared__ int s_c;
-    const int lane = threadIdx.x & 31;
-  // persistent blocks: as many as fit the machine, each takes the next centroid off a device counter until none is left
-  // (k blocks of unequal length in more than one wave would leave the SMs idle behind the stragglers)
-  for (;;) {
-    __syncthreads();
-    if (threadIdx.x == 0) s_c = atomicAdd(work_counter, 1);
-    __syncthreads();
-    const int c = s_c;
-    if (c >= k) break;
-    const int vec = threadIdx.x;  // index of this thread's 16-byte column group inside a row
-    const int col0 = vec * V;
-    const bool active = col0 < d;
-    const int64_t o0 = offsets[c], o1 = offsets[c + 1];
-    const int64_t nmem = o1 - o0;
-    const float cntf = (float)nmem;
-    if (threadIdx.x == 0) hassign[c] = cntf;
+    extern __shared__ __align__(16) uint4 acc_ring[];  // [ACC_WARPS][ACC_GROUPS * ACC_ROWS][32]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint4* my_ring = acc_ring + (size_t)wib * (ACC_GROUPS * ACC_ROWS * 32) + lane;
     const size_t row_vecs = (size_t)d / V;
     const uint4* xv = reinterpret_cast<const uint4*>(x);
-    uint4* my_ring = acc_ring + threadIdx.x;
-    const int stride = blockDim.x;
-    float acc[V], cold[V];
+    const int n_items = k * n_chunks;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(work_counter, 1);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= n_items) break;
+        const int c = order[item / n_chunks];
+        const int chunk = item - (item / n_chunks) * n_chunks;
+        const int vec = chunk * 32 + lane;  // this lane's 16-byte column group inside a row
+        const int col0 = vec * V;
+        const bool active = col0 < d;
+        const int64_t o0 = offsets[c], o1 = offsets[c + 1];
+        const int64_t nmem = o1 - o0;
+        const float cntf = (float)nmem;
+        if (chunk == 0 && lane == 0) hassign[c] = cntf;
+        float acc[V], cold[V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-        acc[j] = 0.f;
-        cold[j] = (OBJ && active) ? cent_old[(size_t)c * d + col0 + j] : 0.f;
-    }
-    double dsum = 0.0;
-    const int64_t ngroups = (nmem + ACC_ROWS - 1) / ACC_ROWS;
-    // member id of row (g * ACC_ROWS + lane) of this centroid, for lanes < ACC_ROWS (-1 past the end)
-    auto fetch_ids = [&](int64_t g) -> int64_t {
-        const int64_t o = o0 + g * ACC_ROWS + lane;
-        if (lane >= ACC_ROWS || g >= ngroups || o >= o1) return -1;
-        const int64_t p = members[o];
-        return ids ? ids[p] : p;
-    };
-    auto issue = [&](int64_t g, int64_t my_id) {  // all lanes call it; row ids come from lanes 0..ACC_ROWS-1
-        const int slot0 = (int)(g % ACC_GROUPS) * ACC_ROWS;
-#pragma unroll
-        for (int u = 0; u < ACC_ROWS; ++u) {
-            const int64_t r = __shfl_sync(FULL, my_id, u);
-            if (r >= 0 && active) cp_async16(my_ring + (size_t)(slot0 + u) * stride, xv + (size_t)r * row_vecs + vec);
+        for (int j = 0; j < V; ++j) {
+            acc[j] = 0.f;
+            cold[j] = (OBJ && active) ? cent_old[(size_t)c * d + col0 + j] : 0.f;
         }
-        cp_async_commit();
-    };
-    // prologue: ACC_GROUPS groups in flight, ids of the next one in registers
-    for (int g = 0; g < ACC_GROUPS; ++g) issue(g, fetch_ids(g));
-    int64_t next_ids = fetch_ids(ACC_GROUPS);
-    for (int64_t g = 0; g < ngroups; ++g) {
-        cp_async_wait<ACC_GROUPS - 1>();  // group g has landed (the groups behind it may still be in flight)
-        const int slot0 = (int)(g % ACC_GROUPS) * ACC_ROWS;
-        const int nrows = (int)((nmem - g * ACC_ROWS) < ACC_ROWS ? (nmem - g * ACC_ROWS) : ACC_ROWS);
-        float part = 0.f;
-        if (active) {
+        double dsum = 0.0;
+        const int64_t ngroups = (nmem + ACC_ROWS - 1) / ACC_ROWS;
+        // member row of (group g, lane) for lanes < ACC_ROWS (-1 past the end)
+        auto fetch_ids = [&](int64_t g) -> int64_t {
+            const int64_t o = o0 + g * ACC_ROWS + lane;
+            if (lane >= ACC_ROWS || g >= ngroups || o >= o1) return -1;
+            const int64_t p = members[o];
+            return ids ? ids[p] : p;
+        };
+        auto issue = [&](int64_t g, int64_t my_id) {  // all lanes call it; row ids come from lanes 0..ACC_ROWS-1
+            const int slot0 = (int)(g % ACC_GROUPS) * ACC_ROWS;
 #pragma unroll
             for (int u = 0; u < ACC_ROWS; ++u) {
-                if (u < nrows) {
-                    const uint4 raw = my_ring[(size_t)(slot0 + u) * stride];
-                    float v[V];
-                    if constexpr (BF16) {
-                        v[0] = __uint_as_float(raw.x << 16); v[1] = __uint_as_float(raw.x & 0xffff0000u);
-                        v[2] = __uint_as_float(raw.y << 16); v[3] = __uint_as_float(raw.y & 0xffff0000u);
-                        v[4] = __uint_as_float(raw.z << 16); v[5] = __uint_as_float(raw.z & 0xffff0000u);
-                        v[6] = __uint_as_float(raw.w << 16); v[7] = __uint_as_float(raw.w & 0xffff0000u);
-                    } else {
-                        v[0] = __uint_as_float(raw.x); v[1] = __uint_as_float(raw.y); v[2] = __uint_as_float(raw.z); v[3] = __uint_as_float(raw.w);
-                    }
+                const int64_t r = __shfl_sync(FULL, my_id, u);
+                if (r >= 0 && active) cp_async16(my_ring + (size_t)(slot0 + u) * 32, xv + (size_t)r * row_vecs + vec);
+            }
+            cp_async_commit();
+        };
+        // prologue: ACC_GROUPS groups in flight, the ids of the next TWO groups in registers
+        for (int g = 0; g < ACC_GROUPS; ++g) issue(g, fetch_ids(g));
+        int64_t ids_a = fetch_ids(ACC_GROUPS), ids_b = fetch_ids(ACC_GROUPS + 1);
+        for (int64_t g = 0; g < ngroups; ++g) {
+            cp_async_wait<ACC_GROUPS - 1>();  // group g has landed (the groups behind it may still be in flight)
+            const int slot0 = (int)(g % ACC_GROUPS) * ACC_ROWS;
+            const int nrows = (int)((nmem - g * ACC_ROWS) < ACC_ROWS ? (nmem - g * ACC_ROWS) : ACC_ROWS);
+            float part = 0.f;
+            if (active) {
 #pragma unroll
-                    for (int j = 0; j < V; ++j) acc[j] = __fadd_rn(acc[j], v[j]);
-                    if constexpr (OBJ) {
+                for (int u = 0; u < ACC_ROWS; ++u) {
+                    if (u < nrows) {
+                        const uint4 raw = my_ring[(size_t)(slot0 + u) * 32];
+                        float v[V];
+                        if constexpr (BF16) {
+                            v[0] = __uint_as_float(raw.x << 16); v[1] = __uint_as_float(raw.x & 0xffff0000u);
+                            v[2] = __uint_as_float(raw.y << 16); v[3] = __uint_as_float(raw.y & 0xffff0000u);
+                            v[4] = __uint_as_float(raw.z << 16); v[5] = __uint_as_float(raw.z & 0xffff0000u);
+                            v[6] = __uint_as_float(raw.w << 16); v[7] = __uint_as_float(raw.w & 0xffff0000u);
+                        } else {
+                            v[0] = __uint_as_float(raw.x); v[1] = __uint_as_float(raw.y); v[2] = __uint_as_float(raw.z); v[3] = __uint_as_float(raw.w);
+                        }
 #pragma unroll
-                        for (int j = 0; j < V; ++j) {
-                            const float df = v[j] - cold[j];
-                            part = fmaf(df, df, part);
+                        for (int j = 0; j < V; ++j) acc[j] = __fadd_rn(acc[j], v[j]);
+                        if constexpr (OBJ) {
+#pragma unroll
+                            for (int j = 0; j < V; ++j) {
+                                const float df = v[j] - cold[j];
+                                part = fmaf(df, df, part);
+                            }
                         }
                     }
                 }
             }
+            if constexpr (OBJ) dsum += (double)part;
+            __syncwarp();
+            // refill the slot just consumed with group g + ACC_GROUPS; keep the member ids two groups ahead of the issue
+            issue(g + ACC_GROUPS, ids_a);
+            ids_a = ids_b;
+            ids_b = fetch_ids(g + ACC_GROUPS + 2);
         }
-        if constexpr (OBJ) dsum += (double)part;
-        // refill the slot just consumed with group g + ACC_GROUPS, then fetch the ids of the one after it
-        issue(g + ACC_GROUPS, next_ids);
-        next_ids = fetch_ids(g + ACC_GROUPS + 1);
-    }
-    cp_async_wait<0>();
-    if (active) {
-        float norm = 1.f;
-        if (normalize && nmem > 0) norm = __fdiv_rn(1.0f, cntf);
+        cp_async_wait<0>();
+        if (active) {
+            float norm = 1.f;
+            if (normalize && nmem > 0) norm = __fdiv_rn(1.0f, cntf);
 #pragma unroll
-        for (int j = 0; j < V; ++j) cent_out[(size_t)c * d + col0 + j] = (normalize && nmem > 0) ? __fmul_rn(acc[j], norm) : acc[j];
-    }
-    if constexpr (OBJ) {
+            for (int j = 0; j < V; ++j) cent_out[(size_t)c * d + col0 + j] = (normalize && nmem > 0) ? __fmul_rn(acc[j], norm) : acc[j];
+        }
+        if constexpr (OBJ) {
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) dsum += __shfl_xor_sync(FULL, dsum, off);
-        if (lane == 0 && dsum != 0.0) atomicAdd(obj, dsum);
+            for (int off = 16; off >= 1; off >>= 1) dsum += __shfl_xor_sync(FULL, dsum, off);
+            if (lane == 0 && dsum != 0.0) atomicAdd(obj, dsum);
+        }
+        __syncwarp();
     }
-  }
 }
 
 // generic shapes (row size not a multiple of 16 bytes): thread (c, j) sums column j over the members in point order
@@ -454,89 +480,95 @@ __global__ void km_accumulate_kernel(const void* x, int dtype, int d, const int6
 // its size (rejection loop over cj = 0, 1, ... with rng.rand_float() = mt() / float(mt.max())), the two copies are perturbed
 // symmetrically and the size is shared. The draws depend on the sizes left by earlier splits, so the walk is sequential;
 // thread 0 draws, the block copies.
-struct DevMt19937 {
-    uint32_t* mt;
-    int idx;
-    __device__ void seed(uint32_t s) {
-        mt[0] = s;
-        for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
-        idx = 624;
-    }
-    __device__ uint32_t next() {
-        if (idx >= 624) {
-            for (int i = 0; i < 624; ++i) {
-                const uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
-                mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-            }
-            idx = 0;
-        }
-        uint32_t y = mt[idx++];
-        y ^= y >> 11;
-        y ^= (y << 7) & 0x9d2c5680u;
-        y ^= (y << 15) & 0xefc60000u;
-        y ^= y >> 18;
-        return y;
-    }
-};
-
-constexpr int SPLIT_SMEM_K = 4096;  // cluster sizes + draw probabilities are walked from shared memory up to this many centroids
+// The draws depend on the sizes left by earlier splits, so clusters are visited sequentially; WITHIN one visit the rejection walk
+// is parallel: the 624 outputs of an MT19937 state are produced by the whole block (the twist in three dependent phases), every
+// thread tests one (draw, candidate) pair of the walk, and the first acceptance in walk order wins (block-wide minimum).
+__device__ __forceinline__ uint32_t mt_mix(uint32_t a, uint32_t b) {
+    const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
 
 __global__ void __launch_bounds__(256) km_split_kernel(int d, int k, int64_t n, float* hassign, float* centroids) {
-    __shared__ uint32_t s_mt[624];
-    __shared__ int s_cj;
-    __shared__ float s_h[SPLIT_SMEM_K];
-    __shared__ float s_p[SPLIT_SMEM_K];  // p[c] = (float)((h[c] - 1.0) / (float)(n - k)), kept current as sizes change
+    __shared__ uint32_t s_mt[624], s_old[624];
+    __shared__ float s_r[624];  // rng.rand_float() = mt() / float(mt.max()) of the current state's outputs
+    __shared__ int s_pos, s_found;
+    const int tid = threadIdx.x;
     int any = 0;
-    for (int c = threadIdx.x; c < k; c += blockDim.x) any |= hassign[c] == 0.f;
+    for (int c = tid; c < k; c += blockDim.x) any |= hassign[c] == 0.f;
     if (!__syncthreads_or(any)) return;
-    float* h = hassign;
-    const double denom = (double)(float)(n - k);
-    const bool in_smem = k <= SPLIT_SMEM_K;
-    if (in_smem) {  // the rejection walk reads one probability per draw: keep them next to the single drawing thread
-        for (int c = threadIdx.x; c < k; c += blockDim.x) {
-            s_h[c] = hassign[c];
-            s_p[c] = (float)(((double)s_h[c] - 1.0) / denom);
-        }
-        h = s_h;
+    if (tid == 0) {  // std::mt19937(1234)
+        s_mt[0] = 1234u;
+        for (int i = 1; i < 624; ++i) s_mt[i] = 1812433253u * (s_mt[i - 1] ^ (s_mt[i - 1] >> 30)) + (uint32_t)i;
+        s_pos = 624;  // no output generated yet
     }
-    DevMt19937 rng{s_mt, 624};
-    if (threadIdx.x == 0) rng.seed(1234u);
     __syncthreads();
     const double EPS = 1 / 1024.;
+    const double denom = (double)(float)(n - k);
     for (int ci = 0; ci < k; ++ci) {
-        if (h[ci] != 0.f) continue;  // block-uniform (sizes are only written between barriers)
-        if (threadIdx.x == 0) {
-            int cj = 0;
-            for (;; cj = (cj + 1) % k) {
-                // float p = (hassign[cj] - 1.0) / (float)(n - k);  float r = rng.rand_float();
-                const float p = in_smem ? s_p[cj] : (float)(((double)h[cj] - 1.0) / denom);
-                const float r = __fdiv_rn(__uint2float_rn(rng.next()), 4294967296.0f);
-                if (r < p) break;
+        if (hassign[ci] != 0.f) continue;  // block-uniform (sizes are only written between barriers)
+        // for (cj = 0; true; cj = (cj + 1) % k) { p = (hassign[cj] - 1.0) / (float)(n - k); r = rng.rand_float(); if (r < p) break; }
+        int64_t tries = 0;
+        int cj = 0;
+        for (;;) {
+            if (s_pos >= 624) {  // next state: mt[i] = mt[i+397 mod 624] ^ mix(mt[i], mt[i+1]) with already-updated sources for i >= 227
+                for (int i = tid; i < 624; i += blockDim.x) s_old[i] = s_mt[i];
+                __syncthreads();
+                for (int i = tid; i < 227; i += blockDim.x) s_mt[i] = s_old[i + 397] ^ mt_mix(s_old[i], s_old[i + 1]);
+                __syncthreads();
+                for (int i = 227 + tid; i < 454; i += blockDim.x) s_mt[i] = s_mt[i - 227] ^ mt_mix(s_old[i], s_old[i + 1]);
+                __syncthreads();
+                for (int i = 454 + tid; i < 623; i += blockDim.x) s_mt[i] = s_mt[i - 227] ^ mt_mix(s_old[i], s_old[i + 1]);
+                __syncthreads();
+                if (tid == 0) {
+                    s_mt[623] = s_mt[396] ^ mt_mix(s_old[623], s_mt[0]);
+                    s_pos = 0;
+                }
+                __syncthreads();
+                for (int i = tid; i < 624; i += blockDim.x) s_r[i] = __fdiv_rn(__uint2float_rn(mt_temper(s_mt[i])), 4294967296.0f);
+                __syncthreads();
             }
-            s_cj = cj;
+            const int pos = s_pos, avail = 624 - pos;
+            if (tid == 0) s_found = 0x7fffffff;
+            __syncthreads();
+            for (int j = tid; j < avail; j += blockDim.x) {
+                const int c = (int)((tries + j) % k);
+                const float p = (float)(((double)hassign[c] - 1.0) / denom);
+                if (s_r[pos + j] < p) atomicMin(&s_found, j);
+            }
+            __syncthreads();
+            const int f = s_found;
+            __syncthreads();
+            if (f != 0x7fffffff) {
+                cj = (int)((tries + f) % k);
+                if (tid == 0) s_pos = pos + f + 1;
+                __syncthreads();
+                break;
+            }
+            tries += avail;
+            if (tid == 0) s_pos = 624;
+            __syncthreads();
         }
-        __syncthreads();
-        const int cj = s_cj;
-        for (int j = threadIdx.x; j < d; j += blockDim.x) {
+        for (int j = tid; j < d; j += blockDim.x) {
             const float src = centroids[(size_t)cj * d + j];
             const double up = 1 + EPS, down = 1 - EPS;
             centroids[(size_t)ci * d + j] = (float)((double)src * ((j % 2 == 0) ? up : down));
             centroids[(size_t)cj * d + j] = (float)((double)src * ((j % 2 == 0) ? down : up));
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            const float hv = h[cj] / 2;
-            h[ci] = hv;
-            h[cj] -= hv;
-            if (in_smem) {
-                s_p[ci] = (float)(((double)h[ci] - 1.0) / denom);
-                s_p[cj] = (float)(((double)h[cj] - 1.0) / denom);
-            }
+        if (tid == 0) {
+            const float hv = hassign[cj] / 2;
+            hassign[ci] = hv;
+            hassign[cj] -= hv;
         }
         __syncthreads();
     }
-    if (h != hassign)
-        for (int c = threadIdx.x; c < k; c += blockDim.x) hassign[c] = s_h[c];
 }
 
 // searchable view of the fp32 centroid matrix; the filter operand matches the point dtype (bf16 points -> bf16 copy).
@@ -698,25 +730,29 @@ int update_centroids(b2_index* idx, const void* x, const int64_t* row_ids, int64
     km_fill_kernel<<<(unsigned)nb, 32, smem, st>>>(assign, n, L, k, w.blk.as<int32_t>(), w.offsets.as<int64_t>(), w.members.as<int32_t>());
     B2_LAUNCH_CHECK();
     const int V = idx->dtype == B2_BF16 ? 8 : 4;
-    const bool vec_ok = d % V == 0 && d / V <= 256 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    const bool vec_ok = d % V == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     if (vec_ok) {
-        const int threads = (int)round_up(d / V, 32);
-        const size_t ring = (size_t)ACC_GROUPS * ACC_ROWS * threads * sizeof(uint4);
+        const int n_chunks = (int)ceil_div(d / V, 32);
+        const size_t ring = (size_t)ACC_WARPS * ACC_GROUPS * ACC_ROWS * 32 * sizeof(uint4);
         const bool want_obj = cent_old != nullptr;
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, idx->device);
         B2_TRY(w.scalar.ensure(64));
+        B2_TRY(w.order.ensure((size_t)k * sizeof(int32_t)));
         int* counter = reinterpret_cast<int*>(w.scalar.as<char>() + 48);
         B2_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+        km_order_kernel<<<1, 1024, 0, st>>>(w.totals.as<int32_t>(), k, w.order.as<int32_t>());
+        B2_LAUNCH_CHECK();
 #define B2_ACC_LAUNCH(BF, OB)                                                                                                     \
     do {                                                                                                                          \
         auto kern = km_accumulate_vec_kernel<BF, OB>;                                                                             \
-        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring)); /* ring + static > 48 KB */  \
+        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));                              \
         int per_sm = 1;                                                                                                           \
-        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, ring));                                     \
-        const int grid = (int)std::min<int64_t>(k, (int64_t)std::max(per_sm, 1) * sms);                                           \
-        kern<<<grid, threads, ring, st>>>(x, d, row_ids, w.members.as<int32_t>(), w.offsets.as<int64_t>(), cent_old, cent_out,    \
-                                          w.hassign.as<float>(), obj, normalize, k, counter);                                     \
+        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ACC_WARPS * 32, ring));                              \
+        const int grid = (int)std::min<int64_t>(ceil_div((int64_t)k * n_chunks, ACC_WARPS), (int64_t)std::max(per_sm, 1) * sms);  \
+        kern<<<grid, ACC_WARPS * 32, ring, st>>>(x, d, row_ids, w.members.as<int32_t>(), w.offsets.as<int64_t>(),                  \
+                                                 w.order.as<int32_t>(), cent_old, cent_out, w.hassign.as<float>(), obj, normalize, \
+                                                 k, n_chunks, counter);                                                           \
     } while (0)
         if (idx->dtype == B2_BF16) {
             if (want_obj) B2_ACC_LAUNCH(true, true);

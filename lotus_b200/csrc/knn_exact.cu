@@ -817,7 +817,7 @@ __global__ void exact_l2_assigned_kernel(const void* pts, int dtype, int64_t m, 
 // Row-sharded search, stage 1: lower[q] = (the j-th best filter score among this shard's candidates) - eps, a lower bound on the
 // exact scores of j rows of this shard. After an all-reduce(MIN) over the ranks with j = ceil(k / ranks), ranks * j >= k rows of
 // the index are known to score at least that much. Warp per query; up to 32 * LB_R candidate entries.
-constexpr int LB_R = 16;
+constexpr int LB_R = 32;
 __global__ void shard_lower_bound_kernel(const float* cand_score, const int32_t* cand_id, int64_t nq, int n_lists, int list_len, int j,
                                          const float* qnorm2, float max_norm, float rel_eps, int metric, float* lower) {
     const int lane = threadIdx.x & 31;

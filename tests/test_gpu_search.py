@@ -248,7 +248,7 @@ def test_staged_sharded_search_emulated_in_one_process(gpu, metric, dtype):
     result must equal the single-index oracle, and the hint must actually prune (fewer exact re-scores than the plain search)."""
     import torch
     dev = torch.device("cuda", 0)
-    x, q = gauss(24_000, 96, 200 + metric), gauss(700, 96, 201)
+    x, q = gauss(24_000, 96, 200 + metric), gauss(6000, 96, 201)   # enough queries that the filter needs few corpus splits
     k, G = 32, 3
     if dtype == "bf16":
         xb, qb = gpu.f32_to_bf16_bits(x), gpu.f32_to_bf16_bits(q)
