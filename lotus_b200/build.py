@@ -46,8 +46,10 @@ def _compile(src: str) -> str:
 
 def build(force: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime():
-        return LIB
+    objs_now = [os.path.join(OBJ, os.path.basename(s)[:-3] + ".o") for s in sources()]
+    fresh = all(os.path.exists(o) and os.path.getmtime(o) >= _deps_mtime() for o in objs_now)  # a library newer than the sources is not
+    if not force and fresh and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(o) for o in objs_now):  # enough: it may have
+        return LIB                                                                                    # been linked from stale objects
     if force:
         for f in glob.glob(os.path.join(OBJ, "*.o")):
             os.remove(f)

@@ -304,9 +304,9 @@ __global__ void km_fill_kernel(const int64_t* assign, int64_t n, int64_t L, int 
 // 5M x 768, DRAM 18 %, SMs active 29 % of the time (tail of the largest clusters), 41 % of stall samples on the first use of a
 // loaded row; v2, the same shape with a cp.async ring: no better (6.6 ms) — the per-centroid chain, not the load depth, was the bound.
 // With OBJ the same pass accumulates sum_members ||x - c_old||^2 (fp32 partials per group, summed in fp64: fp64 issue is scarce).
-constexpr int ACC_ROWS = 8;    // rows per cp.async group
-constexpr int ACC_GROUPS = 4;  // groups in flight
-constexpr int ACC_WARPS = 4;   // warps per block (each with its own 16 KB ring)
+constexpr int ACC_ROWS = 8;     // rows per cp.async group
+constexpr int ACC_GROUPS = 12;  // groups in flight: 96 rows x 512 B per warp — a chain must hide ~2 us of DRAM latency at ~30 ns per row
+constexpr int ACC_WARPS = 4;    // warps per block (each with its own 48 KB ring: one block per SM, one warp per scheduler)
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -367,25 +367,31 @@ __global__ void __launch_bounds__(ACC_WARPS * 32) km_accumulate_vec_kernel(const
         }
         double dsum = 0.0;
         const int64_t ngroups = (nmem + ACC_ROWS - 1) / ACC_ROWS;
-        // member row of (group g, lane) for lanes < ACC_ROWS (-1 past the end)
-        auto fetch_ids = [&](int64_t g) -> int64_t {
-            const int64_t o = o0 + g * ACC_ROWS + lane;
-            if (lane >= ACC_ROWS || g >= ngroups || o >= o1) return -1;
+        // member rows are fetched 32 at a time (one coalesced load = 4 groups), three such batches ahead of the issue point
+        constexpr int GPB = 32 / ACC_ROWS;  // groups per id batch
+        auto fetch_batch = [&](int64_t b) -> int64_t {  // lane l: member row (b * 32 + l) of this centroid, -1 past the end
+            const int64_t o = o0 + b * 32 + lane;
+            if (o >= o1) return -1;
             const int64_t p = members[o];
             return ids ? ids[p] : p;
         };
-        auto issue = [&](int64_t g, int64_t my_id) {  // all lanes call it; row ids come from lanes 0..ACC_ROWS-1
+        auto issue = [&](int64_t g, int64_t batch_ids) {  // all lanes call it; row u of group g sits in lane (g % GPB) * ACC_ROWS + u
             const int slot0 = (int)(g % ACC_GROUPS) * ACC_ROWS;
+            const int lane0 = (int)(g % GPB) * ACC_ROWS;
 #pragma unroll
             for (int u = 0; u < ACC_ROWS; ++u) {
-                const int64_t r = __shfl_sync(FULL, my_id, u);
+                const int64_t r = __shfl_sync(FULL, batch_ids, lane0 + u);
                 if (r >= 0 && active) cp_async16(my_ring + (size_t)(slot0 + u) * 32, xv + (size_t)r * row_vecs + vec);
             }
             cp_async_commit();
         };
-        // prologue: ACC_GROUPS groups in flight, the ids of the next TWO groups in registers
-        for (int g = 0; g < ACC_GROUPS; ++g) issue(g, fetch_ids(g));
-        int64_t ids_a = fetch_ids(ACC_GROUPS), ids_b = fetch_ids(ACC_GROUPS + 1);
+        // prologue: ACC_GROUPS groups in flight (ACC_GROUPS / GPB id batches), then three batches of ids in registers
+        static_assert(ACC_GROUPS % GPB == 0, "the prologue issues whole id batches");
+        for (int b = 0; b < ACC_GROUPS / GPB; ++b) {
+            const int64_t bi = fetch_batch(b);
+            for (int gg = 0; gg < GPB; ++gg) issue((int64_t)b * GPB + gg, bi);
+        }
+        int64_t ids_a = fetch_batch(ACC_GROUPS / GPB), ids_b = fetch_batch(ACC_GROUPS / GPB + 1), ids_c = fetch_batch(ACC_GROUPS / GPB + 2);
         for (int64_t g = 0; g < ngroups; ++g) {
             cp_async_wait<ACC_GROUPS - 1>();  // group g has landed (the groups behind it may still be in flight)
             const int slot0 = (int)(g % ACC_GROUPS) * ACC_ROWS;
@@ -419,10 +425,14 @@ __global__ void __launch_bounds__(ACC_WARPS * 32) km_accumulate_vec_kernel(const
             }
             if constexpr (OBJ) dsum += (double)part;
             __syncwarp();
-            // refill the slot just consumed with group g + ACC_GROUPS; keep the member ids two groups ahead of the issue
-            issue(g + ACC_GROUPS, ids_a);
-            ids_a = ids_b;
-            ids_b = fetch_ids(g + ACC_GROUPS + 2);
+            // refill the slot just consumed with group g + ACC_GROUPS (its ids are in ids_a); rotate the id batches every GPB groups
+            const int64_t gi = g + ACC_GROUPS;
+            issue(gi, ids_a);
+            if ((gi % GPB) == GPB - 1) {
+                ids_a = ids_b;
+                ids_b = ids_c;
+                ids_c = fetch_batch(gi / GPB + 3);
+            }
         }
         cp_async_wait<0>();
         if (active) {
