@@ -305,8 +305,8 @@ __global__ void km_fill_kernel(const int64_t* assign, int64_t n, int64_t L, int 
 // loaded row; v2, the same shape with a cp.async ring: no better (6.6 ms) — the per-centroid chain, not the load depth, was the bound.
 // With OBJ the same pass accumulates sum_members ||x - c_old||^2 (fp32 partials per group, summed in fp64: fp64 issue is scarce).
 constexpr int ACC_ROWS = 8;     // rows per cp.async group
-constexpr int ACC_GROUPS = 12;  // groups in flight: 96 rows x 512 B per warp — a chain must hide ~2 us of DRAM latency at ~30 ns per row
-constexpr int ACC_WARPS = 4;    // warps per block (each with its own 48 KB ring: one block per SM, one warp per scheduler)
+constexpr int ACC_GROUPS = 8;   // groups in flight: 64 rows x 512 B per warp — a chain must hide ~2 us of DRAM latency at ~40 ns per row
+constexpr int ACC_WARPS = 6;    // warps per block (each with its own 32 KB ring: one block of 192 KB per SM)
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -369,61 +369,77 @@ __global__ void __launch_bounds__(ACC_WARPS * 32) km_accumulate_vec_kernel(const
         const int64_t ngroups = (nmem + ACC_ROWS - 1) / ACC_ROWS;
         // member rows are fetched 32 at a time (one coalesced load = 4 groups), three such batches ahead of the issue point
         constexpr int GPB = 32 / ACC_ROWS;  // groups per id batch
-        auto fetch_batch = [&](int64_t b) -> int64_t {  // lane l: member row (b * 32 + l) of this centroid, -1 past the end
+        auto fetch_batch = [&](int64_t b) -> int32_t {  // lane l: member row (b * 32 + l) of this centroid, -1 past the end
             const int64_t o = o0 + b * 32 + lane;
             if (o >= o1) return -1;
-            const int64_t p = members[o];
-            return ids ? ids[p] : p;
+            const int32_t p = members[o];
+            return ids ? (int32_t)ids[p] : p;  // row numbers fit 32 bits (the filter's ids are 32-bit too)
         };
-        auto issue = [&](int64_t g, int64_t batch_ids) {  // all lanes call it; row u of group g sits in lane (g % GPB) * ACC_ROWS + u
-            const int slot0 = (int)(g % ACC_GROUPS) * ACC_ROWS;
+        const char* xb = reinterpret_cast<const char*>(x) + (size_t)vec * 16;
+        const size_t row_bytes = row_vecs * 16;
+        auto issue = [&](int64_t g, int32_t batch_ids) {  // all lanes call it; row u of group g sits in lane (g % GPB) * ACC_ROWS + u
+            uint4* dst = my_ring + (size_t)((int)(g % ACC_GROUPS) * ACC_ROWS) * 32;
             const int lane0 = (int)(g % GPB) * ACC_ROWS;
 #pragma unroll
             for (int u = 0; u < ACC_ROWS; ++u) {
-                const int64_t r = __shfl_sync(FULL, batch_ids, lane0 + u);
-                if (r >= 0 && active) cp_async16(my_ring + (size_t)(slot0 + u) * 32, xv + (size_t)r * row_vecs + vec);
+                const int32_t r = __shfl_sync(FULL, batch_ids, lane0 + u);
+                if (r >= 0 && active) cp_async16(dst + u * 32, xb + (size_t)(uint32_t)r * row_bytes);
             }
             cp_async_commit();
+        };
+        float part[V];  // objective partials, one chain per column (a single chain over the 64 products of a group was the critical path)
+#pragma unroll
+        for (int j = 0; j < V; ++j) part[j] = 0.f;
+        auto consume_row = [&](const uint4& raw) {
+            float v[V];
+            if constexpr (BF16) {
+                v[0] = __uint_as_float(raw.x << 16); v[1] = __uint_as_float(raw.x & 0xffff0000u);
+                v[2] = __uint_as_float(raw.y << 16); v[3] = __uint_as_float(raw.y & 0xffff0000u);
+                v[4] = __uint_as_float(raw.z << 16); v[5] = __uint_as_float(raw.z & 0xffff0000u);
+                v[6] = __uint_as_float(raw.w << 16); v[7] = __uint_as_float(raw.w & 0xffff0000u);
+            } else {
+                v[0] = __uint_as_float(raw.x); v[1] = __uint_as_float(raw.y); v[2] = __uint_as_float(raw.z); v[3] = __uint_as_float(raw.w);
+            }
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[j] = __fadd_rn(acc[j], v[j]);
+            if constexpr (OBJ) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const float df = v[j] - cold[j];
+                    part[j] = fmaf(df, df, part[j]);
+                }
+            }
         };
         // prologue: ACC_GROUPS groups in flight (ACC_GROUPS / GPB id batches), then three batches of ids in registers
         static_assert(ACC_GROUPS % GPB == 0, "the prologue issues whole id batches");
         for (int b = 0; b < ACC_GROUPS / GPB; ++b) {
-            const int64_t bi = fetch_batch(b);
+            const int32_t bi = fetch_batch(b);
             for (int gg = 0; gg < GPB; ++gg) issue((int64_t)b * GPB + gg, bi);
         }
-        int64_t ids_a = fetch_batch(ACC_GROUPS / GPB), ids_b = fetch_batch(ACC_GROUPS / GPB + 1), ids_c = fetch_batch(ACC_GROUPS / GPB + 2);
+        int32_t ids_a = fetch_batch(ACC_GROUPS / GPB), ids_b = fetch_batch(ACC_GROUPS / GPB + 1), ids_c = fetch_batch(ACC_GROUPS / GPB + 2);
         for (int64_t g = 0; g < ngroups; ++g) {
             cp_async_wait<ACC_GROUPS - 1>();  // group g has landed (the groups behind it may still be in flight)
-            const int slot0 = (int)(g % ACC_GROUPS) * ACC_ROWS;
+            const uint4* src = my_ring + (size_t)((int)(g % ACC_GROUPS) * ACC_ROWS) * 32;
             const int nrows = (int)((nmem - g * ACC_ROWS) < ACC_ROWS ? (nmem - g * ACC_ROWS) : ACC_ROWS);
-            float part = 0.f;
             if (active) {
+                if (nrows == ACC_ROWS) {
 #pragma unroll
-                for (int u = 0; u < ACC_ROWS; ++u) {
-                    if (u < nrows) {
-                        const uint4 raw = my_ring[(size_t)(slot0 + u) * 32];
-                        float v[V];
-                        if constexpr (BF16) {
-                            v[0] = __uint_as_float(raw.x << 16); v[1] = __uint_as_float(raw.x & 0xffff0000u);
-                            v[2] = __uint_as_float(raw.y << 16); v[3] = __uint_as_float(raw.y & 0xffff0000u);
-                            v[4] = __uint_as_float(raw.z << 16); v[5] = __uint_as_float(raw.z & 0xffff0000u);
-                            v[6] = __uint_as_float(raw.w << 16); v[7] = __uint_as_float(raw.w & 0xffff0000u);
-                        } else {
-                            v[0] = __uint_as_float(raw.x); v[1] = __uint_as_float(raw.y); v[2] = __uint_as_float(raw.z); v[3] = __uint_as_float(raw.w);
-                        }
-#pragma unroll
-                        for (int j = 0; j < V; ++j) acc[j] = __fadd_rn(acc[j], v[j]);
-                        if constexpr (OBJ) {
-#pragma unroll
-                            for (int j = 0; j < V; ++j) {
-                                const float df = v[j] - cold[j];
-                                part = fmaf(df, df, part);
-                            }
-                        }
-                    }
+                    for (int u = 0; u < ACC_ROWS; ++u) consume_row(src[u * 32]);
+                } else {
+                    for (int u = 0; u < nrows; ++u) consume_row(src[u * 32]);
                 }
             }
-            if constexpr (OBJ) dsum += (double)part;
+            if constexpr (OBJ) {
+                if ((g & 7) == 7 || g + 1 == ngroups) {  // fold the fp32 partials into the fp64 total every 64 rows
+                    float t = 0.f;
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        t += part[j];
+                        part[j] = 0.f;
+                    }
+                    dsum += (double)t;
+                }
+            }
             __syncwarp();
             // refill the slot just consumed with group g + ACC_GROUPS (its ids are in ids_a); rotate the id batches every GPB groups
             const int64_t gi = g + ACC_GROUPS;
