@@ -32,11 +32,11 @@ namespace b2 {
 
 struct KmWork {
     DevBuf cent[2], cent_filt, cent_norm2, scalar, pts, pts_norm2, train, train_norm2, assign, members, offsets, totals, blk, hassign, ids,
-        obj, flag_ids, flag_count, hard_ids, order, sub, sub_dis, sub_assign, fin_assign, fin_dis, perm;
+        obj, flag_ids, flag_count, hard_ids, order, dbg, sub, sub_dis, sub_assign, fin_assign, fin_dis, perm;
     HostBuf h_count;
     void release() {
         DevBuf* all[] = {&cent[0], &cent[1], &cent_filt, &cent_norm2, &scalar, &pts, &pts_norm2, &train, &train_norm2, &assign, &members,
-                         &offsets, &totals, &blk, &hassign, &ids, &obj, &flag_ids, &flag_count, &hard_ids, &order, &sub, &sub_dis, &sub_assign, &fin_assign,
+                         &offsets, &totals, &blk, &hassign, &ids, &obj, &flag_ids, &flag_count, &hard_ids, &order, &dbg, &sub, &sub_dis, &sub_assign, &fin_assign,
                          &fin_dis, &perm};
         for (DevBuf* b : all) b->release();
         h_count.release();
@@ -305,11 +305,17 @@ __global__ void km_fill_kernel(const int64_t* assign, int64_t n, int64_t L, int 
 // loaded row; v2, the same shape with a cp.async ring: no better (6.6 ms) — the per-centroid chain, not the load depth, was the bound.
 // With OBJ the same pass accumulates sum_members ||x - c_old||^2 (fp32 partials per group, summed in fp64: fp64 issue is scarce).
 constexpr int ACC_ROWS = 8;     // rows per cp.async group
-constexpr int ACC_GROUPS = 8;   // groups in flight: 64 rows x 512 B per warp — a chain must hide ~2 us of DRAM latency at ~40 ns per row
-constexpr int ACC_WARPS = 6;    // warps per block (each with its own 32 KB ring: one block of 192 KB per SM)
+constexpr int ACC_GROUPS = 8;   // groups in flight: 64 rows per warp — a chain must hide ~2 us of DRAM latency at ~30 ns per row
+constexpr int ACC_SMEM = 192 * 1024;  // ring memory per SM; a warp's ring is ACC_GROUPS x ACC_ROWS x 32 lanes x LB bytes
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+template <int LB>
+__device__ __forceinline__ void cp_async_lane(void* smem_dst, const void* gsrc) {
+    if constexpr (LB == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+    else if constexpr (LB == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -333,36 +339,47 @@ __global__ void km_order_kernel(const int32_t* totals, int k, int32_t* order) {
     for (int c = threadIdx.x; c < k; c += blockDim.x) order[atomicAdd(&s_base[32 - __clz(max(totals[c], 0))], 1)] = c;
 }
 
-template <bool BF16, bool OBJ>
-__global__ void __launch_bounds__(ACC_WARPS * 32) km_accumulate_vec_kernel(const void* x, int d, const int64_t* ids, const int32_t* members,
-                                                                           const int64_t* offsets, const int32_t* order, const float* cent_old,
-                                                                           float* cent_out, float* hassign, double* obj, int normalize, int k,
-                                                                           int n_chunks, int* work_counter) {
-    constexpr int V = BF16 ? 8 : 4;
-    extern __shared__ __align__(16) uint4 acc_ring[];  // [ACC_WARPS][ACC_GROUPS * ACC_ROWS][32]
+template <int LB> struct LaneWord;
+template <> struct LaneWord<16> { using T = uint4; };
+template <> struct LaneWord<8> { using T = uint2; };
+template <> struct LaneWord<4> { using T = uint32_t; };
+
+// LB = bytes of a member row per lane (4, 8 or 16): a warp covers 32 * LB contiguous bytes of every member row. Small LB = more,
+// shorter-per-row chains: the time of the pass is bounded below by (largest cluster) x (cycles per row of ONE warp), and the
+// largest cluster is ~10x the mean while Lloyd converges on the benchmark mixture (48k of 5M rows at k = 1024).
+template <bool BF16, bool OBJ, int LB>
+__global__ void __launch_bounds__(256) km_accumulate_vec_kernel(const void* x, int d, const int64_t* ids, const int32_t* members,
+                                                                const int64_t* offsets, const int32_t* order, const float* cent_old,
+                                                                float* cent_out, float* hassign, double* obj, int normalize, int k,
+                                                                int n_chunks, int* work_counter, long long* dbg) {
+    constexpr int V = BF16 ? LB / 2 : LB / 4;  // columns per lane
+    using Word = typename LaneWord<LB>::T;
+    extern __shared__ __align__(16) uint8_t acc_ring_raw[];  // [warps][ACC_GROUPS * ACC_ROWS][32] words
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    uint4* my_ring = acc_ring + (size_t)wib * (ACC_GROUPS * ACC_ROWS * 32) + lane;
-    const size_t row_vecs = (size_t)d / V;
-    const uint4* xv = reinterpret_cast<const uint4*>(x);
+    Word* my_ring = reinterpret_cast<Word*>(acc_ring_raw) + (size_t)wib * (ACC_GROUPS * ACC_ROWS * 32) + lane;
+    const size_t row_bytes = (size_t)d * (BF16 ? 2 : 4);
+    const int row_words = (int)(row_bytes / LB);
     const int n_items = k * n_chunks;
     for (;;) {
         int item = 0;
         if (lane == 0) item = atomicAdd(work_counter, 1);
         item = __shfl_sync(FULL, item, 0);
         if (item >= n_items) break;
+        const long long dbg_t0 = dbg ? clock64() : 0;
         const int c = order[item / n_chunks];
         const int chunk = item - (item / n_chunks) * n_chunks;
-        const int vec = chunk * 32 + lane;  // this lane's 16-byte column group inside a row
-        const int col0 = vec * V;
-        const bool active = col0 < d;
+        const int word = chunk * 32 + lane;  // this lane's LB-byte slice inside a row
+        const int col0 = word * V;
+        const bool active = word < row_words;
         const int64_t o0 = offsets[c], o1 = offsets[c + 1];
         const int64_t nmem = o1 - o0;
         const float cntf = (float)nmem;
         if (chunk == 0 && lane == 0) hassign[c] = cntf;
-        float acc[V], cold[V];
+        float acc[V], cold[V], part[V];  // sums, old centroid (objective), objective partials (one chain per column)
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             acc[j] = 0.f;
+            part[j] = 0.f;
             cold[j] = (OBJ && active) ? cent_old[(size_t)c * d + col0 + j] : 0.f;
         }
         double dsum = 0.0;
@@ -375,30 +392,29 @@ __global__ void __launch_bounds__(ACC_WARPS * 32) km_accumulate_vec_kernel(const
             const int32_t p = members[o];
             return ids ? (int32_t)ids[p] : p;  // row numbers fit 32 bits (the filter's ids are 32-bit too)
         };
-        const char* xb = reinterpret_cast<const char*>(x) + (size_t)vec * 16;
-        const size_t row_bytes = row_vecs * 16;
+        const char* xb = reinterpret_cast<const char*>(x) + (size_t)word * LB;
         auto issue = [&](int64_t g, int32_t batch_ids) {  // all lanes call it; row u of group g sits in lane (g % GPB) * ACC_ROWS + u
-            uint4* dst = my_ring + (size_t)((int)(g % ACC_GROUPS) * ACC_ROWS) * 32;
+            Word* dst = my_ring + (size_t)((int)(g % ACC_GROUPS) * ACC_ROWS) * 32;
             const int lane0 = (int)(g % GPB) * ACC_ROWS;
 #pragma unroll
             for (int u = 0; u < ACC_ROWS; ++u) {
                 const int32_t r = __shfl_sync(FULL, batch_ids, lane0 + u);
-                if (r >= 0 && active) cp_async16(dst + u * 32, xb + (size_t)(uint32_t)r * row_bytes);
+                if (r >= 0 && active) cp_async_lane<LB>(dst + u * 32, xb + (size_t)(uint32_t)r * row_bytes);
             }
             cp_async_commit();
         };
-        float part[V];  // objective partials, one chain per column (a single chain over the 64 products of a group was the critical path)
-#pragma unroll
-        for (int j = 0; j < V; ++j) part[j] = 0.f;
-        auto consume_row = [&](const uint4& raw) {
+        auto consume_row = [&](const Word& raw) {
             float v[V];
+            const uint32_t* w32 = reinterpret_cast<const uint32_t*>(&raw);
             if constexpr (BF16) {
-                v[0] = __uint_as_float(raw.x << 16); v[1] = __uint_as_float(raw.x & 0xffff0000u);
-                v[2] = __uint_as_float(raw.y << 16); v[3] = __uint_as_float(raw.y & 0xffff0000u);
-                v[4] = __uint_as_float(raw.z << 16); v[5] = __uint_as_float(raw.z & 0xffff0000u);
-                v[6] = __uint_as_float(raw.w << 16); v[7] = __uint_as_float(raw.w & 0xffff0000u);
+#pragma unroll
+                for (int t = 0; t < LB / 4; ++t) {
+                    v[2 * t] = __uint_as_float(w32[t] << 16);
+                    v[2 * t + 1] = __uint_as_float(w32[t] & 0xffff0000u);
+                }
             } else {
-                v[0] = __uint_as_float(raw.x); v[1] = __uint_as_float(raw.y); v[2] = __uint_as_float(raw.z); v[3] = __uint_as_float(raw.w);
+#pragma unroll
+                for (int t = 0; t < LB / 4; ++t) v[t] = __uint_as_float(w32[t]);
             }
 #pragma unroll
             for (int j = 0; j < V; ++j) acc[j] = __fadd_rn(acc[j], v[j]);
@@ -419,7 +435,7 @@ __global__ void __launch_bounds__(ACC_WARPS * 32) km_accumulate_vec_kernel(const
         int32_t ids_a = fetch_batch(ACC_GROUPS / GPB), ids_b = fetch_batch(ACC_GROUPS / GPB + 1), ids_c = fetch_batch(ACC_GROUPS / GPB + 2);
         for (int64_t g = 0; g < ngroups; ++g) {
             cp_async_wait<ACC_GROUPS - 1>();  // group g has landed (the groups behind it may still be in flight)
-            const uint4* src = my_ring + (size_t)((int)(g % ACC_GROUPS) * ACC_ROWS) * 32;
+            const Word* src = my_ring + (size_t)((int)(g % ACC_GROUPS) * ACC_ROWS) * 32;
             const int nrows = (int)((nmem - g * ACC_ROWS) < ACC_ROWS ? (nmem - g * ACC_ROWS) : ACC_ROWS);
             if (active) {
                 if (nrows == ACC_ROWS) {
@@ -461,6 +477,14 @@ __global__ void __launch_bounds__(ACC_WARPS * 32) km_accumulate_vec_kernel(const
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) dsum += __shfl_xor_sync(FULL, dsum, off);
             if (lane == 0 && dsum != 0.0) atomicAdd(obj, dsum);
+        }
+        if (dbg && lane == 0) {  // B2_KM_DEBUG: (rows, cycles, start clock, SM) of every work item
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            dbg[4 * (size_t)item + 0] = nmem;
+            dbg[4 * (size_t)item + 1] = clock64() - dbg_t0;
+            dbg[4 * (size_t)item + 2] = dbg_t0;
+            dbg[4 * (size_t)item + 3] = smid;
         }
         __syncwarp();
     }
@@ -755,11 +779,17 @@ int update_centroids(b2_index* idx, const void* x, const int64_t* row_ids, int64
     B2_LAUNCH_CHECK();
     km_fill_kernel<<<(unsigned)nb, 32, smem, st>>>(assign, n, L, k, w.blk.as<int32_t>(), w.offsets.as<int64_t>(), w.members.as<int32_t>());
     B2_LAUNCH_CHECK();
-    const int V = idx->dtype == B2_BF16 ? 8 : 4;
-    const bool vec_ok = d % V == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    // bytes of a row per lane (B2_KM_LANE_BYTES = 4 | 8 | 16 for experiments; 4 = shortest per-row chains)
+    static const int lane_bytes_env = [] { const char* e = getenv("B2_KM_LANE_BYTES"); const int v = e ? atoi(e) : 4; return (v == 8 || v == 16) ? v : 4; }();
+    const size_t row_bytes_total = (size_t)d * esize(idx->dtype);
+    int LB = lane_bytes_env;
+    while (LB > 4 && (row_bytes_total % LB != 0 || (reinterpret_cast<uintptr_t>(x) % LB) != 0)) LB /= 2;
+    const bool vec_ok = row_bytes_total % LB == 0 && (reinterpret_cast<uintptr_t>(x) % LB) == 0;
     if (vec_ok) {
-        const int n_chunks = (int)ceil_div(d / V, 32);
-        const size_t ring = (size_t)ACC_WARPS * ACC_GROUPS * ACC_ROWS * 32 * sizeof(uint4);
+        const int n_chunks = (int)ceil_div((int64_t)(row_bytes_total / LB), 32);
+        const size_t warp_ring = (size_t)ACC_GROUPS * ACC_ROWS * 32 * LB;
+        const int warps = (int)std::min<size_t>(8, std::max<size_t>(1, (64 * 1024) / warp_ring));  // <= 64 KB of ring per block
+        const size_t ring = warp_ring * warps;
         const bool want_obj = cent_old != nullptr;
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, idx->device);
@@ -769,25 +799,52 @@ int update_centroids(b2_index* idx, const void* x, const int64_t* row_ids, int64
         B2_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
         km_order_kernel<<<1, 1024, 0, st>>>(w.totals.as<int32_t>(), k, w.order.as<int32_t>());
         B2_LAUNCH_CHECK();
-#define B2_ACC_LAUNCH(BF, OB)                                                                                                     \
+        static const bool dbg_on = [] { const char* e = getenv("B2_KM_DEBUG"); return e && atoi(e) != 0; }();
+        long long* dbg = nullptr;
+        if (dbg_on) {
+            B2_TRY(w.dbg.ensure((size_t)k * n_chunks * 4 * sizeof(long long)));
+            dbg = w.dbg.as<long long>();
+        }
+#define B2_ACC_LAUNCH(BF, OB, LBV)                                                                                                \
     do {                                                                                                                          \
-        auto kern = km_accumulate_vec_kernel<BF, OB>;                                                                             \
+        auto kern = km_accumulate_vec_kernel<BF, OB, LBV>;                                                                        \
         B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));                              \
         int per_sm = 1;                                                                                                           \
-        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ACC_WARPS * 32, ring));                              \
-        const int grid = (int)std::min<int64_t>(ceil_div((int64_t)k * n_chunks, ACC_WARPS), (int64_t)std::max(per_sm, 1) * sms);  \
-        kern<<<grid, ACC_WARPS * 32, ring, st>>>(x, d, row_ids, w.members.as<int32_t>(), w.offsets.as<int64_t>(),                  \
-                                                 w.order.as<int32_t>(), cent_old, cent_out, w.hassign.as<float>(), obj, normalize, \
-                                                 k, n_chunks, counter);                                                           \
+        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, ring));                                  \
+        per_sm = std::max(1, std::min<int>(per_sm, (int)(ACC_SMEM / ring)));                                                      \
+        const int grid = (int)std::min<int64_t>(ceil_div((int64_t)k * n_chunks, warps), (int64_t)per_sm * sms);                   \
+        kern<<<grid, warps * 32, ring, st>>>(x, d, row_ids, w.members.as<int32_t>(), w.offsets.as<int64_t>(), w.order.as<int32_t>(), \
+                                             cent_old, cent_out, w.hassign.as<float>(), obj, normalize, k, n_chunks, counter, dbg); \
+    } while (0)
+#define B2_ACC_LB(BF, OB)                                          \
+    do {                                                           \
+        if (LB == 16) B2_ACC_LAUNCH(BF, OB, 16);                   \
+        else if (LB == 8) B2_ACC_LAUNCH(BF, OB, 8);                \
+        else B2_ACC_LAUNCH(BF, OB, 4);                             \
     } while (0)
         if (idx->dtype == B2_BF16) {
-            if (want_obj) B2_ACC_LAUNCH(true, true);
-            else B2_ACC_LAUNCH(true, false);
+            if (want_obj) B2_ACC_LB(true, true);
+            else B2_ACC_LB(true, false);
         } else {
-            if (want_obj) B2_ACC_LAUNCH(false, true);
-            else B2_ACC_LAUNCH(false, false);
+            if (want_obj) B2_ACC_LB(false, true);
+            else B2_ACC_LB(false, false);
         }
+#undef B2_ACC_LB
 #undef B2_ACC_LAUNCH
+        if (dbg) {
+            std::vector<long long> h((size_t)k * n_chunks * 4);
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+            long long rows_tot = 0;
+            size_t worst = 0;
+            for (size_t i = 0; i < (size_t)k * n_chunks; ++i) {
+                rows_tot += h[4 * i];
+                if (h[4 * i + 1] > h[4 * worst + 1]) worst = i;
+            }
+            fprintf(stderr, "[b2 km accumulate dbg] lane bytes %d, items %d, rows/item mean %.0f | slowest item: %lld rows in %lld cycles (%.0f cycles/row), SM %lld\n",
+                    LB, k * n_chunks, (double)rows_tot / (k * n_chunks), h[4 * worst], h[4 * worst + 1],
+                    (double)h[4 * worst + 1] / std::max<long long>(h[4 * worst], 1), h[4 * worst + 3]);
+        }
     } else {
         dim3 grid((unsigned)k, (unsigned)ceil_div(d, 128));
         km_accumulate_kernel<<<grid, 128, 0, st>>>(x, idx->dtype, d, row_ids, w.members.as<int32_t>(), w.offsets.as<int64_t>(), cent_old,
