@@ -308,14 +308,16 @@ constexpr int ACC_ROWS = 8;     // rows per cp.async group
 constexpr int ACC_GROUPS = 8;   // groups in flight: 64 rows per warp — a chain must hide ~2 us of DRAM latency at ~30 ns per row
 constexpr int ACC_SMEM = 192 * 1024;  // ring memory per SM; a warp's ring is ACC_GROUPS x ACC_ROWS x 32 lanes x LB bytes
 
+// predicated, branch-free: a branch around every copy serialises the eight row copies of a group behind each other's shuffle
 template <int LB>
-__device__ __forceinline__ void cp_async_lane(void* smem_dst, const void* gsrc) {
+__device__ __forceinline__ void cp_async_lane(void* smem_dst, const void* gsrc, bool pred) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
     if constexpr (LB == 16)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}" ::"r"(dst), "l"(gsrc), "r"((int)pred) : "memory");
     else if constexpr (LB == 8)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 8;\n\t}" ::"r"(dst), "l"(gsrc), "r"((int)pred) : "memory");
     else
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 4;\n\t}" ::"r"(dst), "l"(gsrc), "r"((int)pred) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -396,11 +398,12 @@ __global__ void __launch_bounds__(256) km_accumulate_vec_kernel(const void* x, i
         auto issue = [&](int64_t g, int32_t batch_ids) {  // all lanes call it; row u of group g sits in lane (g % GPB) * ACC_ROWS + u
             Word* dst = my_ring + (size_t)((int)(g % ACC_GROUPS) * ACC_ROWS) * 32;
             const int lane0 = (int)(g % GPB) * ACC_ROWS;
+            int32_t r[ACC_ROWS];
 #pragma unroll
-            for (int u = 0; u < ACC_ROWS; ++u) {
-                const int32_t r = __shfl_sync(FULL, batch_ids, lane0 + u);
-                if (r >= 0 && active) cp_async_lane<LB>(dst + u * 32, xb + (size_t)(uint32_t)r * row_bytes);
-            }
+            for (int u = 0; u < ACC_ROWS; ++u) r[u] = __shfl_sync(FULL, batch_ids, lane0 + u);
+#pragma unroll
+            for (int u = 0; u < ACC_ROWS; ++u)
+                cp_async_lane<LB>(dst + u * 32, xb + (size_t)(uint32_t)max(r[u], 0) * row_bytes, r[u] >= 0 && active);
             cp_async_commit();
         };
         auto consume_row = [&](const Word& raw) {
