@@ -305,8 +305,7 @@ __global__ void km_fill_kernel(const int64_t* assign, int64_t n, int64_t L, int 
 // loaded row; v2, the same shape with a cp.async ring: no better (6.6 ms) — the per-centroid chain, not the load depth, was the bound.
 // With OBJ the same pass accumulates sum_members ||x - c_old||^2 (fp32 partials per group, summed in fp64: fp64 issue is scarce).
 constexpr int ACC_ROWS = 8;     // rows per cp.async group
-constexpr int ACC_GROUPS = 8;   // groups in flight: 64 rows per warp — a chain must hide ~2 us of DRAM latency at ~30 ns per row
-constexpr int ACC_SMEM = 192 * 1024;  // ring memory per SM; a warp's ring is ACC_GROUPS x ACC_ROWS x 32 lanes x LB bytes
+constexpr int ACC_SMEM = 192 * 1024;  // ring memory per SM; a warp's ring is NG groups x ACC_ROWS x 32 lanes x LB bytes
 
 // predicated, branch-free: a branch around every copy serialises the eight row copies of a group behind each other's shuffle
 template <int LB>
@@ -349,7 +348,7 @@ template <> struct LaneWord<4> { using T = uint32_t; };
 // LB = bytes of a member row per lane (4, 8 or 16): a warp covers 32 * LB contiguous bytes of every member row. Small LB = more,
 // shorter-per-row chains: the time of the pass is bounded below by (largest cluster) x (cycles per row of ONE warp), and the
 // largest cluster is ~10x the mean while Lloyd converges on the benchmark mixture (48k of 5M rows at k = 1024).
-template <bool BF16, bool OBJ, int LB>
+template <bool BF16, bool OBJ, int LB, int ACC_GROUPS>
 __global__ void __launch_bounds__(256) km_accumulate_vec_kernel(const void* x, int d, const int64_t* ids, const int32_t* members,
                                                                 const int64_t* offsets, const int32_t* order, const float* cent_old,
                                                                 float* cent_out, float* hassign, double* obj, int normalize, int k,
@@ -790,8 +789,11 @@ int update_centroids(b2_index* idx, const void* x, const int64_t* row_ids, int64
     const bool vec_ok = row_bytes_total % LB == 0 && (reinterpret_cast<uintptr_t>(x) % LB) == 0;
     if (vec_ok) {
         const int n_chunks = (int)ceil_div((int64_t)(row_bytes_total / LB), 32);
-        const size_t warp_ring = (size_t)ACC_GROUPS * ACC_ROWS * 32 * LB;
-        const int warps = (int)std::min<size_t>(8, std::max<size_t>(1, (64 * 1024) / warp_ring));  // <= 64 KB of ring per block
+        // cp.async groups in flight per warp (B2_KM_RING_GROUPS = 8 | 32 for experiments): rows in flight = 8 x groups
+        static const int ring_groups = [] { const char* e = getenv("B2_KM_RING_GROUPS"); const int v = e ? atoi(e) : 32; return v == 8 ? 8 : 32; }();
+        const int NG = ring_groups;
+        const size_t warp_ring = (size_t)NG * ACC_ROWS * 32 * LB;
+        const int warps = (int)std::min<size_t>(8, std::max<size_t>(1, (64 * 1024) / warp_ring));  // <= 64 KB of ring per block (one warp may exceed it)
         const size_t ring = warp_ring * warps;
         const bool want_obj = cent_old != nullptr;
         int sms = 148;
@@ -808,9 +810,9 @@ int update_centroids(b2_index* idx, const void* x, const int64_t* row_ids, int64
             B2_TRY(w.dbg.ensure((size_t)k * n_chunks * 4 * sizeof(long long)));
             dbg = w.dbg.as<long long>();
         }
-#define B2_ACC_LAUNCH(BF, OB, LBV)                                                                                                \
+#define B2_ACC_LAUNCH(BF, OB, LBV, NGV)                                                                                           \
     do {                                                                                                                          \
-        auto kern = km_accumulate_vec_kernel<BF, OB, LBV>;                                                                        \
+        auto kern = km_accumulate_vec_kernel<BF, OB, LBV, NGV>;                                                                   \
         B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));                              \
         int per_sm = 1;                                                                                                           \
         B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, ring));                                  \
@@ -819,11 +821,11 @@ int update_centroids(b2_index* idx, const void* x, const int64_t* row_ids, int64
         kern<<<grid, warps * 32, ring, st>>>(x, d, row_ids, w.members.as<int32_t>(), w.offsets.as<int64_t>(), w.order.as<int32_t>(), \
                                              cent_old, cent_out, w.hassign.as<float>(), obj, normalize, k, n_chunks, counter, dbg); \
     } while (0)
-#define B2_ACC_LB(BF, OB)                                          \
-    do {                                                           \
-        if (LB == 16) B2_ACC_LAUNCH(BF, OB, 16);                   \
-        else if (LB == 8) B2_ACC_LAUNCH(BF, OB, 8);                \
-        else B2_ACC_LAUNCH(BF, OB, 4);                             \
+#define B2_ACC_LB(BF, OB)                                                          \
+    do {                                                                           \
+        if (LB == 16) { if (NG == 8) B2_ACC_LAUNCH(BF, OB, 16, 8); else B2_ACC_LAUNCH(BF, OB, 16, 32); } \
+        else if (LB == 8) { if (NG == 8) B2_ACC_LAUNCH(BF, OB, 8, 8); else B2_ACC_LAUNCH(BF, OB, 8, 32); } \
+        else { if (NG == 8) B2_ACC_LAUNCH(BF, OB, 4, 8); else B2_ACC_LAUNCH(BF, OB, 4, 32); }            \
     } while (0)
         if (idx->dtype == B2_BF16) {
             if (want_obj) B2_ACC_LB(true, true);
