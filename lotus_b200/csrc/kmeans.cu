@@ -300,9 +300,17 @@ __global__ void km_fill_kernel(const int64_t* assign, int64_t n, int64_t L, int 
 //     have already landed;
 //   * balance: cluster sizes are far from equal while Lloyd is converging (some centroids hold 4x the mean), and the longest
 //     chain bounds the pass — warps pull items off a device counter in DECREASING cluster size (km_order_kernel).
-// History (profiles/r2_kmeans_accumulate_*): v1, one block per centroid with 16 row loads per lane in registers: 5.2 ms at
-// 5M x 768, DRAM 18 %, SMs active 29 % of the time (tail of the largest clusters), 41 % of stall samples on the first use of a
-// loaded row; v2, the same shape with a cp.async ring: no better (6.6 ms) — the per-centroid chain, not the load depth, was the bound.
+// History (profiles/r2_kmeans_accumulate_variants.txt, all at 5M x 768 bf16, k = 1024, one pass):
+//   r1  thread per (centroid, column), 2-byte loads ................................ 9.4 ms
+//   v1  block per centroid, 16 row loads per lane in registers ..................... 5.3 ms  (DRAM 18 %, SMs busy 29 % of the time)
+//   v2  same shape, cp.async ring of 32 rows per block ............................. 6.6 ms  (the per-centroid chain, not load depth, bounds it)
+//   v3/v4  warp per (centroid, 512 B chunk), largest cluster first, 32 / 96-row rings  7.4 / 5.5 ms
+//   v5  + per-column objective partials (one fp32 chain over a group's 64 products was the critical path), 32-bit ids,
+//       unpredicated full groups, 6 warps x 64-row rings per SM .................... 3.6 ms   <- this kernel
+//   also tried: 4- and 8-byte lanes (4x / 2x as many, thinner chains), 256-row rings, branch-free predicated copies, TMA bulk
+//   copies (cp.async.bulk + mbarrier, one copy per row slice): 3.6-5.0 ms, none better. Per-item counters (B2_KM_DEBUG=1) show
+//   why: the largest cluster holds ~48k of the 5M rows (10x the mean) and its chain advances at 110-170 cycles per row whatever
+//   the variant, so the pass cannot end before ~48k x 140 cycles = 3.5 ms; the other 3071 items finish long before.
 // With OBJ the same pass accumulates sum_members ||x - c_old||^2 (fp32 partials per group, summed in fp64: fp64 issue is scarce).
 constexpr int ACC_ROWS = 8;     // rows per cp.async group
 constexpr int ACC_SMEM = 192 * 1024;  // ring memory per SM; a warp's ring is NG groups x ACC_ROWS x 32 lanes x LB bytes
@@ -481,201 +489,6 @@ __global__ void __launch_bounds__(256) km_accumulate_vec_kernel(const void* x, i
             if (lane == 0 && dsum != 0.0) atomicAdd(obj, dsum);
         }
         if (dbg && lane == 0) {  // B2_KM_DEBUG: (rows, cycles, start clock, SM) of every work item
-            unsigned smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            dbg[4 * (size_t)item + 0] = nmem;
-            dbg[4 * (size_t)item + 1] = clock64() - dbg_t0;
-            dbg[4 * (size_t)item + 2] = dbg_t0;
-            dbg[4 * (size_t)item + 3] = smid;
-        }
-        __syncwarp();
-    }
-}
-
-// ---- the same pass with TMA bulk copies (cp.async.bulk, completion on an mbarrier) --------------------------------------------
-// Why: with cp.async per lane every ROW costs every lane ~8 instructions to issue (shuffle, clamp, 64-bit address, predicate, copy).
-// The pass is bounded by (rows of the largest cluster) x (cycles per row of the ONE warp that owns a chunk of it), and a lone warp
-// retires ~0.2 instructions per cycle on this dependent stream: ~110-170 cycles per row measured whatever the lane width and the
-// ring depth (profiles/r2_kmeans_accumulate_*). Here a GROUP of 8 member rows is issued by 8 lanes with one bulk copy each
-// (32 * LB contiguous bytes of the row -> the warp's ring slot) and one arrive.expect_tx; the consumers wait on the group's
-// mbarrier phase. Per-row work left for a lane: one shared-memory load, the unpack and the adds.
-__device__ __forceinline__ void km_mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void km_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void km_mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
-    uint32_t done = 0, spins = 0;
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (done) break;
-        if (++spins > (1u << 28)) {  // a protocol bug must trap (sticky error the host reports), not hang the GPU
-            printf("b2 km_accumulate_bulk: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void km_bulk_copy(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     (uint32_t)__cvta_generic_to_shared(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
-                 : "memory");
-}
-
-constexpr int BULK_GROUPS = 32;  // groups of ACC_ROWS rows in flight per warp (256 rows)
-
-template <bool BF16, bool OBJ, int LB>
-__global__ void __launch_bounds__(256) km_accumulate_bulk_kernel(const void* x, int d, const int64_t* ids, const int32_t* members,
-                                                                 const int64_t* offsets, const int32_t* order, const float* cent_old,
-                                                                 float* cent_out, float* hassign, double* obj, int normalize, int k,
-                                                                 int n_chunks, int* work_counter, long long* dbg) {
-    constexpr int V = BF16 ? LB / 2 : LB / 4;  // columns per lane
-    constexpr int CH = 32 * LB;                // bytes of a member row per warp
-    using Word = typename LaneWord<LB>::T;
-    extern __shared__ __align__(128) uint8_t bulk_smem[];  // [warps][BULK_GROUPS * ACC_ROWS * CH] rings, then [warps][BULK_GROUPS] barriers
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    uint8_t* ring = bulk_smem + (size_t)wib * (BULK_GROUPS * ACC_ROWS * CH);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bulk_smem + (size_t)nwarps * (BULK_GROUPS * ACC_ROWS * CH)) + (size_t)wib * BULK_GROUPS;
-    if (lane == 0) {
-        for (int i = 0; i < BULK_GROUPS; ++i) km_mbar_init(&bars[i], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const size_t row_bytes = (size_t)d * (BF16 ? 2 : 4);
-    const int row_words = (int)(row_bytes / LB);
-    const int n_items = k * n_chunks;
-    uint32_t gseq = 0;  // groups this warp has issued so far, over all its items: slot = gseq % BULK_GROUPS, parity = (gseq / BULK_GROUPS) & 1
-    for (;;) {
-        int item = 0;
-        if (lane == 0) item = atomicAdd(work_counter, 1);
-        item = __shfl_sync(FULL, item, 0);
-        if (item >= n_items) break;
-        const long long dbg_t0 = dbg ? clock64() : 0;
-        const int c = order[item / n_chunks];
-        const int chunk = item - (item / n_chunks) * n_chunks;
-        const int word = chunk * 32 + lane;
-        const int col0 = word * V;
-        const bool active = word < row_words;
-        const uint32_t chunk_bytes = (uint32_t)min((size_t)CH, row_bytes - (size_t)chunk * CH);  // the last chunk of a row may be short
-        const int64_t o0 = offsets[c], o1 = offsets[c + 1];
-        const int64_t nmem = o1 - o0;
-        const float cntf = (float)nmem;
-        if (chunk == 0 && lane == 0) hassign[c] = cntf;
-        float acc[V], cold[V], part[V];
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-            acc[j] = 0.f;
-            part[j] = 0.f;
-            cold[j] = (OBJ && active) ? cent_old[(size_t)c * d + col0 + j] : 0.f;
-        }
-        double dsum = 0.0;
-        const int64_t ngroups = (nmem + ACC_ROWS - 1) / ACC_ROWS;
-        constexpr int GPB = 32 / ACC_ROWS;
-        auto fetch_batch = [&](int64_t b) -> int32_t {  // lane l: member row (b * 32 + l) of this centroid, -1 past the end
-            const int64_t o = o0 + b * 32 + lane;
-            if (o >= o1) return -1;
-            const int32_t p = members[o];
-            return ids ? (int32_t)ids[p] : p;
-        };
-        const char* xb = reinterpret_cast<const char*>(x) + (size_t)chunk * CH;
-        const uint32_t g0 = gseq;  // sequence number of this item's group 0
-        auto issue = [&](int64_t g, int32_t batch_ids) {  // group g of this item (g < ngroups): 8 lanes copy one row slice each
-            const uint32_t seq = g0 + (uint32_t)g;
-            const int slot = (int)(seq % BULK_GROUPS);
-            const int nrows = (int)((nmem - g * ACC_ROWS) < ACC_ROWS ? (nmem - g * ACC_ROWS) : ACC_ROWS);
-            if (lane == 0) km_mbar_expect_tx(&bars[slot], (uint32_t)nrows * chunk_bytes);
-            __syncwarp();
-            const int u = lane - (int)(g % GPB) * ACC_ROWS;  // this lane's row inside the group, if it holds one
-            if (u >= 0 && u < nrows && batch_ids >= 0)
-                km_bulk_copy(ring + (size_t)(slot * ACC_ROWS + u) * CH, xb + (size_t)(uint32_t)batch_ids * row_bytes, chunk_bytes, &bars[slot]);
-        };
-        auto consume_row = [&](const Word& raw) {
-            float v[V];
-            const uint32_t* w32 = reinterpret_cast<const uint32_t*>(&raw);
-            if constexpr (BF16) {
-#pragma unroll
-                for (int t = 0; t < LB / 4; ++t) {
-                    v[2 * t] = __uint_as_float(w32[t] << 16);
-                    v[2 * t + 1] = __uint_as_float(w32[t] & 0xffff0000u);
-                }
-            } else {
-#pragma unroll
-                for (int t = 0; t < LB / 4; ++t) v[t] = __uint_as_float(w32[t]);
-            }
-#pragma unroll
-            for (int j = 0; j < V; ++j) acc[j] = __fadd_rn(acc[j], v[j]);
-            if constexpr (OBJ) {
-#pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    const float df = v[j] - cold[j];
-                    part[j] = fmaf(df, df, part[j]);
-                }
-            }
-        };
-        // prologue: up to BULK_GROUPS groups in flight; the ids of the next three batches (of 4 groups) in registers
-        static_assert(BULK_GROUPS % GPB == 0, "the prologue issues whole id batches");
-        for (int b = 0; b < BULK_GROUPS / GPB; ++b) {
-            if ((int64_t)b * GPB >= ngroups) break;
-            const int32_t bi = fetch_batch(b);
-            for (int gg = 0; gg < GPB; ++gg)
-                if ((int64_t)b * GPB + gg < ngroups) issue((int64_t)b * GPB + gg, bi);
-        }
-        int32_t ids_a = fetch_batch(BULK_GROUPS / GPB), ids_b = fetch_batch(BULK_GROUPS / GPB + 1), ids_c = fetch_batch(BULK_GROUPS / GPB + 2);
-        for (int64_t g = 0; g < ngroups; ++g) {
-            const uint32_t seq = g0 + (uint32_t)g;
-            const int slot = (int)(seq % BULK_GROUPS);
-            km_mbar_wait(&bars[slot], (seq / BULK_GROUPS) & 1u);  // the group's row slices have landed
-            const Word* src = reinterpret_cast<const Word*>(ring + (size_t)slot * ACC_ROWS * CH) + lane;
-            const int nrows = (int)((nmem - g * ACC_ROWS) < ACC_ROWS ? (nmem - g * ACC_ROWS) : ACC_ROWS);
-            if (active) {
-                if (nrows == ACC_ROWS) {
-#pragma unroll
-                    for (int u = 0; u < ACC_ROWS; ++u) consume_row(src[u * 32]);
-                } else {
-                    for (int u = 0; u < nrows; ++u) consume_row(src[u * 32]);
-                }
-            }
-            if constexpr (OBJ) {
-                if ((g & 7) == 7 || g + 1 == ngroups) {
-                    float t = 0.f;
-#pragma unroll
-                    for (int j = 0; j < V; ++j) {
-                        t += part[j];
-                        part[j] = 0.f;
-                    }
-                    dsum += (double)t;
-                }
-            }
-            __syncwarp();  // every lane has read the slot before it is handed back to the copy engine
-            const int64_t gi = g + BULK_GROUPS;
-            if (gi < ngroups) issue(gi, ids_a);
-            if ((gi % GPB) == GPB - 1) {
-                ids_a = ids_b;
-                ids_b = ids_c;
-                ids_c = fetch_batch(gi / GPB + 3);
-            }
-        }
-        gseq = g0 + (uint32_t)ngroups;
-        if (active) {
-            float norm = 1.f;
-            if (normalize && nmem > 0) norm = __fdiv_rn(1.0f, cntf);
-#pragma unroll
-            for (int j = 0; j < V; ++j) cent_out[(size_t)c * d + col0 + j] = (normalize && nmem > 0) ? __fmul_rn(acc[j], norm) : acc[j];
-        }
-        if constexpr (OBJ) {
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) dsum += __shfl_xor_sync(FULL, dsum, off);
-            if (lane == 0 && dsum != 0.0) atomicAdd(obj, dsum);
-        }
-        if (dbg && lane == 0) {
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
             dbg[4 * (size_t)item + 0] = nmem;
@@ -976,23 +789,25 @@ int update_centroids(b2_index* idx, const void* x, const int64_t* row_ids, int64
     B2_LAUNCH_CHECK();
     km_fill_kernel<<<(unsigned)nb, 32, smem, st>>>(assign, n, L, k, w.blk.as<int32_t>(), w.offsets.as<int64_t>(), w.members.as<int32_t>());
     B2_LAUNCH_CHECK();
-    // bytes of a row per lane (B2_KM_LANE_BYTES = 4 | 8 | 16 for experiments; 4 = shortest per-row chains)
-    static const int lane_bytes_env = [] { const char* e = getenv("B2_KM_LANE_BYTES"); const int v = e ? atoi(e) : 4; return (v == 8 || v == 16) ? v : 4; }();
+    // Bytes of a member row per lane: 16 (a warp covers 512 B of the row, fewest instructions per byte) unless that leaves too few
+    // (centroid, chunk) chains to occupy the machine — few centroids — then 4 (128 B per warp, 4x as many chains).
+    // B2_KM_LANE_BYTES = 4 | 16 overrides. Measured at 5M x 768, k = 1024 (profiles/r2_kmeans_accumulate_variants.txt): the pass is
+    // bounded by the LARGEST cluster's chain (~48k of 5M rows, 10x the mean, while Lloyd converges) at ~110-170 cycles per row of
+    // one warp, whatever the lane width (4 / 8 / 16 B), the ring depth (64 / 256 rows) or the copy mechanism (cp.async / TMA bulk).
+    static const int lane_bytes_env = [] { const char* e = getenv("B2_KM_LANE_BYTES"); const int v = e ? atoi(e) : 0; return (v == 4 || v == 16) ? v : 0; }();
     const size_t row_bytes_total = (size_t)d * esize(idx->dtype);
-    int LB = lane_bytes_env;
-    while (LB > 4 && (row_bytes_total % LB != 0 || (reinterpret_cast<uintptr_t>(x) % LB) != 0)) LB /= 2;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, idx->device);
+    int LB = lane_bytes_env ? lane_bytes_env : ((int64_t)k * (int64_t)ceil_div((int64_t)row_bytes_total, 512) >= 4LL * 6 * sms ? 16 : 4);
+    if (LB == 16 && (row_bytes_total % 16 != 0 || (reinterpret_cast<uintptr_t>(x) % 16) != 0)) LB = 4;
     const bool vec_ok = row_bytes_total % LB == 0 && (reinterpret_cast<uintptr_t>(x) % LB) == 0;
     if (vec_ok) {
         const int n_chunks = (int)ceil_div((int64_t)(row_bytes_total / LB), 32);
-        // cp.async groups in flight per warp (B2_KM_RING_GROUPS = 8 | 32 for experiments): rows in flight = 8 x groups
-        static const int ring_groups = [] { const char* e = getenv("B2_KM_RING_GROUPS"); const int v = e ? atoi(e) : 32; return v == 8 ? 8 : 32; }();
-        const int NG = ring_groups;
+        const int NG = LB == 16 ? 8 : 32;  // cp.async groups of 8 rows in flight per warp: a 32 KB ring either way, 6 warps per SM
         const size_t warp_ring = (size_t)NG * ACC_ROWS * 32 * LB;
-        const int warps = (int)std::min<size_t>(8, std::max<size_t>(1, (64 * 1024) / warp_ring));  // <= 64 KB of ring per block (one warp may exceed it)
+        const int warps = 2;
         const size_t ring = warp_ring * warps;
         const bool want_obj = cent_old != nullptr;
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, idx->device);
         B2_TRY(w.scalar.ensure(64));
         B2_TRY(w.order.ensure((size_t)k * sizeof(int32_t)));
         int* counter = reinterpret_cast<int*>(w.scalar.as<char>() + 48);
@@ -1005,10 +820,6 @@ int update_centroids(b2_index* idx, const void* x, const int64_t* row_ids, int64
             B2_TRY(w.dbg.ensure((size_t)k * n_chunks * 4 * sizeof(long long)));
             dbg = w.dbg.as<long long>();
         }
-        // TMA bulk copies need 16-byte aligned sources and sizes: row pitch and the matrix base (the last chunk of a row may be short)
-        static const bool bulk_env = [] { const char* e = getenv("B2_KM_BULK"); return e ? atoi(e) != 0 : true; }();
-        const bool bulk = bulk_env && row_bytes_total % 16 == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0 && ((32 * LB) % 16) == 0 &&
-                          (row_bytes_total % (32 * LB)) % 16 == 0;
 #define B2_ACC_LAUNCH(BF, OB, LBV, NGV)                                                                                           \
     do {                                                                                                                          \
         auto kern = km_accumulate_vec_kernel<BF, OB, LBV, NGV>;                                                                   \
@@ -1020,29 +831,10 @@ int update_centroids(b2_index* idx, const void* x, const int64_t* row_ids, int64
         kern<<<grid, warps * 32, ring, st>>>(x, d, row_ids, w.members.as<int32_t>(), w.offsets.as<int64_t>(), w.order.as<int32_t>(), \
                                              cent_old, cent_out, w.hassign.as<float>(), obj, normalize, k, n_chunks, counter, dbg); \
     } while (0)
-#define B2_BULK_LAUNCH(BF, OB, LBV)                                                                                               \
-    do {                                                                                                                          \
-        auto kern = km_accumulate_bulk_kernel<BF, OB, LBV>;                                                                       \
-        const size_t wring = (size_t)BULK_GROUPS * ACC_ROWS * 32 * LBV;                                                           \
-        const int bw = (int)std::min<size_t>(8, std::max<size_t>(1, (size_t)ACC_SMEM / wring)); /* one block per SM */            \
-        const size_t bsmem = wring * bw + (size_t)bw * BULK_GROUPS * sizeof(uint64_t);                                            \
-        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));                             \
-        int per_sm = 1;                                                                                                           \
-        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, bw * 32, bsmem));                                    \
-        per_sm = std::max(1, std::min<int>(per_sm, std::max(1, (int)((ACC_SMEM + 4096) / bsmem))));                               \
-        const int grid = (int)std::min<int64_t>(ceil_div((int64_t)k * n_chunks, bw), (int64_t)per_sm * sms);                      \
-        kern<<<grid, bw * 32, bsmem, st>>>(x, d, row_ids, w.members.as<int32_t>(), w.offsets.as<int64_t>(), w.order.as<int32_t>(), \
-                                           cent_old, cent_out, w.hassign.as<float>(), obj, normalize, k, n_chunks, counter, dbg); \
-    } while (0)
-#define B2_ACC_LB(BF, OB)                                                          \
-    do {                                                                           \
-        if (bulk) {                                                                \
-            if (LB == 16) B2_BULK_LAUNCH(BF, OB, 16);                              \
-            else if (LB == 8) B2_BULK_LAUNCH(BF, OB, 8);                           \
-            else B2_BULK_LAUNCH(BF, OB, 4);                                        \
-        } else if (LB == 16) { if (NG == 8) B2_ACC_LAUNCH(BF, OB, 16, 8); else B2_ACC_LAUNCH(BF, OB, 16, 32); } \
-        else if (LB == 8) { if (NG == 8) B2_ACC_LAUNCH(BF, OB, 8, 8); else B2_ACC_LAUNCH(BF, OB, 8, 32); } \
-        else { if (NG == 8) B2_ACC_LAUNCH(BF, OB, 4, 8); else B2_ACC_LAUNCH(BF, OB, 4, 32); }            \
+#define B2_ACC_LB(BF, OB)                              \
+    do {                                               \
+        if (LB == 16) B2_ACC_LAUNCH(BF, OB, 16, 8);    \
+        else B2_ACC_LAUNCH(BF, OB, 4, 32);             \
     } while (0)
         if (idx->dtype == B2_BF16) {
             if (want_obj) B2_ACC_LB(true, true);
@@ -1052,7 +844,6 @@ int update_centroids(b2_index* idx, const void* x, const int64_t* row_ids, int64
             else B2_ACC_LB(false, false);
         }
 #undef B2_ACC_LB
-#undef B2_BULK_LAUNCH
 #undef B2_ACC_LAUNCH
         if (dbg) {
             std::vector<long long> h((size_t)k * n_chunks * 4);
