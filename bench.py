@@ -426,8 +426,8 @@ def main() -> None:
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=str, default="c3", choices=["c3", "c2", "c4", "c5"],
                     help="c3 = the headline (BASELINE.json configs[2]); c2 / c4 / c5 = the secondary configurations")
-    ap.add_argument("--nq", type=int, default=100_000)
-    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--nq", "--queries", dest="nq", type=int, default=100_000)
+    ap.add_argument("--n", "--corpus-rows", dest="n", type=int, default=1_000_000)
     ap.add_argument("--d", type=int, default=768)
     ap.add_argument("--k", type=int, default=32)
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries per CPU-baseline step (0 = about 8-15 s of the host cores)")
