@@ -168,7 +168,8 @@ int search_core(b2_index* idx, const MatView& X_in, int metric, const void* q_de
         float* osc = out_sc + (size_t)q0 * k;
         int64_t* oid = out_id + (size_t)q0 * k;
         const bool two_cta = filter_use_pair(nqc);
-        const int n_splits = filter_choose_splits(nqc, X.n, dev_sms, two_cta, false, min_splits);
+        int units_whole = 0;
+        const int n_splits = filter_choose_splits(nqc, X.n, dev_sms, two_cta, false, min_splits, &units_whole);
         if (n_splits <= 0) {
             set_error("internal: no valid corpus split for k=%d over %lld rows", k, (long long)X.n);
             return B2_EINVAL;
@@ -187,7 +188,7 @@ int search_core(b2_index* idx, const MatView& X_in, int metric, const void* q_de
         if (!q_in_place) B2_TRY(launch_prep_queries(qc, q_dtype, nqc, X.d, idx->q_filt.p, filt_dtype, q_pitch, st));
         B2_CUDA(cudaEventRecord(idx->ev0, st));
         B2_TRY(launch_knn_filter(X, q_filt, q_pitch, nqc, metric, kp, n_splits, two_cta, idx->cand_score.as<float>(),
-                                 idx->cand_id.as<int32_t>(), idx->cand_thr.as<float>(), idx->device, st));
+                                 idx->cand_id.as<int32_t>(), idx->cand_thr.as<float>(), idx->device, st, false, units_whole));
         B2_CUDA(cudaEventRecord(idx->ev1, st));
         B2_TRY(launch_finalize(X, qc, q_dtype, nqc, metric, k, kp, kp / 2, 2 * n_splits, idx->cand_score.as<float>(),
                                idx->cand_id.as<int32_t>(), idx->cand_thr.as<float>(), rel_eps, id_map, id_offset, osc, oid,
@@ -483,7 +484,8 @@ int b2_index_search_stage1_dev(b2_index* idx, const void* q_dev, int64_t nq, int
     int dev_sms = 148;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, idx->device);
     const bool two_cta = filter_use_pair(nq);
-    const int n_splits = use_filter ? filter_choose_splits(nq, X.n, dev_sms, two_cta, false, min_splits) : 0;
+    int units_whole = 0;
+    const int n_splits = use_filter ? filter_choose_splits(nq, X.n, dev_sms, two_cta, false, min_splits, &units_whole) : 0;
     if (!use_filter || two_level || nq > chunk || n_splits <= 0 || 2 * n_splits * (kp / 2) > shard_lower_bound_max_entries() || j > k) {
         return launch_fill_f32(lower_dev, nq, -INFINITY, st);  // stage 2 will run the plain search
     }
@@ -503,7 +505,7 @@ int b2_index_search_stage1_dev(b2_index* idx, const void* q_dev, int64_t nq, int
     B2_TRY(idx->scalar.ensure(64));
     B2_CUDA(cudaEventRecord(idx->ev0, st));
     B2_TRY(launch_knn_filter(X, q_filt, q_pitch, nq, idx->metric, kp, n_splits, two_cta, idx->cand_score.as<float>(), idx->cand_id.as<int32_t>(),
-                             idx->cand_thr.as<float>(), idx->device, st));
+                             idx->cand_thr.as<float>(), idx->device, st, false, units_whole));
     B2_CUDA(cudaEventRecord(idx->ev1, st));
     sg.kp = kp;
     sg.n_splits = n_splits;

@@ -107,9 +107,10 @@ struct SearchWorkspace;
 int filter_kp_for_k(int k);  // candidate-list capacity used for a given k, 0 = k too large for the filter
 int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int64_t nq, int metric, int kp,
                       int n_splits, bool two_cta, float* cand_score, int32_t* cand_id, float* cand_thr, int device,
-                      cudaStream_t stream, bool top1 = false);
+                      cudaStream_t stream, bool top1 = false, int units_whole = 0);
 bool filter_use_pair(int64_t nq);
-int filter_choose_splits(int64_t nq, int64_t n, int num_sms, bool two_cta, bool top1 = false, int min_splits = 1);  // 0: impossible
+int filter_choose_splits(int64_t nq, int64_t n, int num_sms, bool two_cta, bool top1 = false, int min_splits = 1,
+                         int* units_whole = nullptr);  // 0: impossible; *units_whole > 0: two-phase schedule (see the definition)
 int filter_min_splits_for_k(int k);
 int launch_pair_filter(const MatView& X, float thr, int part, int nparts, int32_t* pair_i, int32_t* pair_j,
                        unsigned long long* pair_count, unsigned long long cap, int device, cudaStream_t stream);

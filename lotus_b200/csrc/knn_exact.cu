@@ -317,6 +317,12 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(const Finalize
                 chunk[r] = kk;
             }
             for (int li = lane; li < lists_per_chunk && s0 + li < p.n_splits; li += 32) bound = fmaxf(bound, p.cand_thr[qbase + s0 + li]);
+            {  // lists of a query unit that swept the corpus as ONE item are empty beyond split 0: nothing to sort or fold
+                bool any_key = false;
+#pragma unroll
+                for (int r = 0; r < R; ++r) any_key |= chunk[r] != KEY_WORST;
+                if (!__any_sync(FULL, any_key) && !first) continue;
+            }
             warp_bitonic_sort<R>(chunk, lane);
             if (first) {
 #pragma unroll

@@ -284,6 +284,8 @@ struct FilterParams {
     int32_t n_splits;
     int32_t top1;             // host-side switch only: the TOP1 kernel variant is launched (k-means assignment)
     int32_t tiles_per_split;  // corpus tiles (of 256 rows) per split
+    int32_t units_whole;      // two-phase schedule: the first units_whole query units (a multiple of the worker count) sweep the WHOLE
+                              // corpus as one item each (split 0); only the remaining units are cut into n_splits splits
     int32_t n_ntiles;         // ceil(n / 256)
     // all-pairs (dedup) schedule: the query matrix IS the corpus; an item is one query tile sweeping only the corpus tiles
     // that can hold a column j > i (upper triangle). Query tiles are dealt to the `nparts` ranks in GROUPS of pair_group
@@ -330,7 +332,7 @@ __device__ __forceinline__ Sched make_sched() {
 }
 __device__ __forceinline__ int num_items(const FilterParams& p) {
     if (p.pair_mode) return p.pair_items;
-    return p.n_munits * p.n_splits;
+    return p.units_whole + (p.n_munits - p.units_whole) * p.n_splits;
 }
 template <bool TWO>
 __device__ __forceinline__ void item_range(const FilterParams& p, const Sched& sc, int item, int& m_tile, int& split, int& t0,
@@ -347,11 +349,20 @@ __device__ __forceinline__ void item_range(const FilterParams& p, const Sched& s
         t0 = (lead_tile * BLOCK_M) / BLOCK_N;  // first corpus tile that can contain a column > row
         t1 = p.n_ntiles;
     } else {
-        const int unit = item % p.n_munits;
+        int unit;
+        if (item < p.units_whole) {  // phase A: one worker, one unit, every corpus tile (all workers stream the same tiles in step)
+            unit = item;
+            split = 0;
+            t0 = 0;
+            t1 = p.n_ntiles;
+        } else {  // phase B: the leftover units, unit fastest, cut into n_splits splits to fill the last waves
+            const int j = item - p.units_whole, rem = p.n_munits - p.units_whole;
+            unit = p.units_whole + j % rem;
+            split = j / rem;
+            t0 = split * p.tiles_per_split;
+            t1 = min(t0 + p.tiles_per_split, p.n_ntiles);
+        }
         m_tile = TWO ? 2 * unit + sc.rank : unit;
-        split = item / p.n_munits;
-        t0 = split * p.tiles_per_split;
-        t1 = min(t0 + p.tiles_per_split, p.n_ntiles);
     }
 }
 
@@ -1060,7 +1071,8 @@ bool filter_use_pair(int64_t nq) {
 
 // Number of corpus splits: enough work items to fill the machine, and few idle workers in the last wave.
 // In pair mode a worker is a CTA pair and a query unit is two query tiles.
-int filter_choose_splits(int64_t nq, int64_t n, int num_sms, bool two_cta, bool top1, int min_splits) {
+int filter_choose_splits(int64_t nq, int64_t n, int num_sms, bool two_cta, bool top1, int min_splits, int* units_whole) {
+    if (units_whole) *units_whole = 0;
     {
         static int forced = -1;  // B2_FILTER_SPLITS: experiments only
         if (forced < 0) {
@@ -1094,12 +1106,42 @@ int filter_choose_splits(int64_t nq, int64_t n, int num_sms, bool two_cta, bool 
             best = s;
         }
     }
+    // Two-phase schedule: as many whole waves as possible run ONE unit per worker over the whole corpus (one list warm-up per
+    // wave instead of one per split, and the workers still stream the same corpus tiles in step, which is what keeps them in
+    // L2); only the leftover units (< one per worker) are cut into splits, just fine enough to fill the last waves. On a
+    // 125k-row shard with 100k queries: 5 x (489 + 13) + 2 x (70 + 13) = 2676 tile-times against 16 x (163 + 13) = 2816.
+    static const bool two_phase_on = [] { const char* e = getenv("B2_FILTER_TWO_PHASE"); return e ? atoi(e) != 0 : true; }();
+    const int64_t waves_a = n_units / workers;
+    if (units_whole && two_phase_on && min_splits <= 1 && waves_a >= 1) {
+        const int64_t ua = waves_a * workers, rem = n_units - ua;
+        const double cost_a = (double)waves_a * ((double)n_ntiles + kWarmupTiles);
+        double best2 = 1e300;
+        int s2 = 1;
+        if (rem == 0) {
+            best2 = cost_a;
+        } else {
+            for (int s = 1; s <= 256 && s <= n_ntiles; ++s) {
+                const int64_t tps = ceil_div(n_ntiles, s);
+                if (ceil_div(n_ntiles, tps) != s) continue;
+                const int64_t waves_b = ceil_div(rem * s, workers);
+                const double cost = (cost_a + (double)waves_b * ((double)tps + kWarmupTiles)) * (1.0 + 0.002 * s);
+                if (cost < best2 - 1e-9) {
+                    best2 = cost;
+                    s2 = s;
+                }
+            }
+        }
+        if (best2 < best_cost - 1e-9) {
+            *units_whole = (int)ua;
+            return s2;
+        }
+    }
     return best;
 }
 
 int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int64_t nq, int metric, int kp,
                       int n_splits, bool two_cta, float* cand_score, int32_t* cand_id, float* cand_thr, int device,
-                      cudaStream_t stream, bool top1) {
+                      cudaStream_t stream, bool top1, int units_whole) {
     if (nq <= 0 || X.n <= 0) return B2_OK;
     if (X.n > 0x7fffff00LL || nq > 0x7fffff00LL) {
         set_error("matrix too large for 32-bit row ids (n=%lld nq=%lld)", (long long)X.n, (long long)nq);
@@ -1125,6 +1167,7 @@ int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int
     p.n_ntiles = (int32_t)ceil_div(X.n, BLOCK_N);
     p.tiles_per_split = (int32_t)ceil_div(p.n_ntiles, n_splits);
     p.n_splits = n_splits;
+    p.units_whole = units_whole;
     p.top1 = (top1 && kp == 16) ? 1 : 0;  // register-resident top-2 epilogue: requested by the k-means assignment path only
     p.pair_mode = 0;
     p.part = 0;
@@ -1152,7 +1195,16 @@ int launch_knn_filter(const MatView& X, const void* q_filt, int64_t q_pitch, int
         set_error("internal: empty corpus split (tiles %d, splits %d)", p.n_ntiles, n_splits);
         return B2_EINVAL;
     }
-    const int64_t items = (int64_t)p.n_munits * n_splits;
+    if (units_whole < 0 || units_whole > p.n_munits) {
+        set_error("internal: bad two-phase schedule (%d whole units of %d)", units_whole, p.n_munits);
+        return B2_EINVAL;
+    }
+    const int64_t items = (int64_t)units_whole + (int64_t)(p.n_munits - units_whole) * n_splits;
+    if (units_whole > 0 && n_splits > 1) {
+        // whole units write split 0 only: the other lists of their queries must read as empty (id -1, bound -inf)
+        B2_CUDA(cudaMemsetAsync(cand_id, 0xFF, (size_t)nq * n_splits * kp * sizeof(int32_t), stream));
+        B2_TRY(launch_fill_f32(cand_thr, nq * (int64_t)n_splits * 2, -INFINITY, stream));
+    }
     const bool is_l2 = metric == B2_METRIC_L2;
     if (is_l2 && !X.norm2) {
         set_error("internal: L2 filter without row norms");
