@@ -2,9 +2,15 @@
 
 CPU restatement of the faiss-cpu 1.13 algorithms behind the reference's hot path
 (lotus/vector_store/faiss_vs.py:22-77, lotus/utils.py:61-65). PARITY UNPINNED: faiss itself is
-not available in this image and the reference holds no golden vectors for this path, so the
-restatement is pinned only against hand-derived known answers (tests/golden/) and independent
-numpy cross-checks.
+not available in this image (nor on the GPU box) and the reference holds no golden vectors for this
+path, so the restatement is pinned only against hand-derived known answers (tests/golden/) and
+independent numpy cross-checks. bench.py `faiss_probe()` / `cpu_arms()` switch to the real wheel the
+day `import faiss` succeeds and print the comparison with this restatement.
+
+Besides the canonical oracle (`knn`, `kmeans`, ...: portable build, -ffp-contract=off) this package holds
+the TIMED CPU arms of bench.py: `knn_tiled` (cache-tiled fp32 FMA search, compiled on the host with
+-march=native), `knn_sgemm` (numpy/OpenBLAS sgemm + argpartition) and `cpu_budget()` (affinity capped by
+the cgroup CPU quota).
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this package.
 Nothing under lotus_b200/ imports it.
