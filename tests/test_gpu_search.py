@@ -293,3 +293,14 @@ def test_staged_sharded_search_emulated_in_one_process(gpu, metric, dtype):
     assert np.array_equal((got & np.uint64(0xffffffff)).astype(np.int64), I0)
     for s in shards:
         s.close()
+
+
+@pytest.mark.parametrize("metric,dtype,k", [(0, "bf16", 10), (1, "bf16", 32), (0, "f32", 5)])
+def test_two_phase_schedule_whole_waves_and_split_remainder(gpu, metric, dtype, k):
+    """Batches of at least one query unit per worker (>= 74 CTA pairs x 256 queries) take the two-phase schedule: whole waves of
+    (one unit per worker x the whole corpus) and a remainder cut into corpus splits whose extra candidate lists are empty for the
+    whole-wave units. 40,000 queries = 157 units = 2 whole waves + 9 leftover units: EVERY query is checked against the oracle,
+    so both phases (and the unit that is half empty at the end of the batch) are covered."""
+    x, q = gauss(20_000, 64, 300 + k), gauss(40_000, 64, 301 + k)
+    st = check(gpu, x, q, k, metric, dtype, expect_filter=True)
+    assert st["fallback_queries"] <= 40, st
