@@ -188,6 +188,12 @@ B2_API int b2_kmeans_accumulate(b2_index* idx, const int64_t* ids, int64_t m, co
  * vectors that came out of a bf16 index (faiss_vs.py:38-41 -> sem_sim_join.py:130-134) in their exact 2-byte form. */
 B2_API int b2_host_f32_to_bf16(const float* x, int64_t count, uint16_t* out, int32_t* all_exact);
 
+/* The filter kernel's work schedule for a shape (no device work; used by the CPU tests): kp = candidate-list capacity (0 = the
+ * shape goes to the dense path), n_splits = corpus splits, units_whole = leading query units that sweep the whole corpus as one
+ * item each (two-phase schedule), two_cta = CTA-pair mode. */
+B2_API int b2_debug_filter_plan(int64_t nq, int64_t n, int32_t k, int32_t num_sms, int32_t* kp, int32_t* n_splits,
+                         int32_t* units_whole, int32_t* two_cta);
+
 /* ---- instrumentation ---------------------------------------------------------------------------------- */
 /* counters since the last b2_stats_reset(): [0] kernels launched by this library, [1] queries answered,
  * [2] queries that took the exact dense fallback, [3] tcgen05 filter launches, [4] rows rescored exactly,

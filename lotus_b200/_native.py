@@ -20,7 +20,7 @@ SYMBOLS = [
     "b2_abi_version", "b2_last_error", "b2_device_count", "b2_max_k", "b2_index_create", "b2_index_free",
     "b2_index_ntotal", "b2_index_dim", "b2_index_dtype", "b2_index_metric", "b2_index_device", "b2_index_data_dev",
     "b2_index_search", "b2_index_search_dev", "b2_merge_topk_dev", "b2_index_search_packed_dev", "b2_merge_topk_packed_dev", "b2_index_search_stage1_dev", "b2_index_search_stage2_packed_dev", "b2_index_gather", "b2_threshold_pairs",
-    "b2_connected_components", "b2_kmeans", "b2_kmeans_assign", "b2_kmeans_accumulate", "b2_kmeans_assign_dev", "b2_kmeans_accumulate_dev", "b2_stats", "b2_stats_reset", "b2_last_filter_ms", "b2_host_f32_to_bf16",
+    "b2_connected_components", "b2_kmeans", "b2_kmeans_assign", "b2_kmeans_accumulate", "b2_kmeans_assign_dev", "b2_kmeans_accumulate_dev", "b2_stats", "b2_stats_reset", "b2_last_filter_ms", "b2_host_f32_to_bf16", "b2_debug_filter_plan",
 ]
 
 
@@ -90,6 +90,8 @@ def lib() -> ctypes.CDLL:
     L.b2_kmeans_accumulate_dev.argtypes = [vp, vp, i64, vp, i32, vp, vp, vp, vp, vp]
     L.b2_host_f32_to_bf16.restype = c.c_int
     L.b2_host_f32_to_bf16.argtypes = [vp, i64, vp, c.POINTER(i32)]
+    L.b2_debug_filter_plan.restype = c.c_int
+    L.b2_debug_filter_plan.argtypes = [i64, i64, i32, i32, c.POINTER(i32), c.POINTER(i32), c.POINTER(i32), c.POINTER(i32)]
     L.b2_stats.restype = c.c_int
     L.b2_stats.argtypes = [c.POINTER(i64), i32]
     L.b2_stats_reset.restype = None
@@ -111,6 +113,13 @@ def device_count() -> int:
 def require_device() -> None:
     if device_count() == 0:
         raise RuntimeError("lotus_b200 needs a B200 (sm_100) GPU; none is visible and there is no CPU fallback")
+
+
+def filter_plan(nq: int, n: int, k: int, num_sms: int = 148) -> dict:
+    """The filter kernel's schedule for a shape (host logic only, no device needed)."""
+    kp, ns, uw, two = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    check(lib().b2_debug_filter_plan(nq, n, k, num_sms, ctypes.byref(kp), ctypes.byref(ns), ctypes.byref(uw), ctypes.byref(two)))
+    return {"kp": kp.value, "n_splits": ns.value, "units_whole": uw.value, "two_cta": bool(two.value)}
 
 
 def stats() -> dict:

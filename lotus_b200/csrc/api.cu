@@ -638,6 +638,19 @@ int b2_host_f32_to_bf16(const float* x, int64_t count, uint16_t* out, int32_t* a
     return B2_OK;
 }
 
+// The filter's work schedule for a (queries, rows, k) shape on `num_sms` SMs — no device work: lets the CPU test-suite check that
+// every (query unit, corpus tile) pair is covered exactly once for the shapes the GPU tests do not reach.
+int b2_debug_filter_plan(int64_t nq, int64_t n, int32_t k, int32_t num_sms, int32_t* kp, int32_t* n_splits, int32_t* units_whole,
+                         int32_t* two_cta) {
+    if (nq <= 0 || n <= 0 || k <= 0 || num_sms <= 0 || !kp || !n_splits || !units_whole || !two_cta) { set_error("bad arguments"); return B2_EINVAL; }
+    *kp = filter_kp_for_k(k);
+    *two_cta = filter_use_pair(nq) ? 1 : 0;
+    int uw = 0;
+    *n_splits = *kp ? filter_choose_splits(nq, n, num_sms, *two_cta != 0, false, filter_min_splits_for_k(k), &uw) : 0;
+    *units_whole = uw;
+    return B2_OK;
+}
+
 int b2_stats(int64_t* out, int32_t cap) {
     int n = cap < 8 ? cap : 8;
     for (int i = 0; i < n; ++i) out[i] = g_stats[i];

@@ -447,3 +447,79 @@ def test_sem_search_k_doubling_branch_equals_the_ids_branch_and_rerank_reorders(
         assert only["t"].tolist() == sub["t"].tolist()[::-1][:2]
     finally:
         lotus.settings.configure(reranker=None)
+
+
+def _schedule_items(plan, nq, n, workers):
+    """Python mirror of knn_filter_sm100.cu item_range / num_items (non-pair mode): -> per worker the list of (unit, split, t0, t1)."""
+    n_mtiles = -(-nq // 128)
+    n_units = -(-n_mtiles // 2) if plan["two_cta"] else n_mtiles
+    n_ntiles = -(-n // 256)
+    s, uw = plan["n_splits"], plan["units_whole"]
+    tps = -(-n_ntiles // s)
+    total = uw + (n_units - uw) * s
+    out = [[] for _ in range(workers)]
+    for item in range(total):
+        if item < uw:
+            unit, split, t0, t1 = item, 0, 0, n_ntiles
+        else:
+            j, rem = item - uw, n_units - uw
+            unit, split = uw + j % rem, j // rem
+            t0, t1 = split * tps, min(split * tps + tps, n_ntiles)
+        out[item % workers].append((unit, split, t0, t1))
+    return out, n_units, n_ntiles
+
+
+@pytest.mark.parametrize("nq,n", [(100_000, 1_000_000), (100_000, 500_000), (100_000, 250_000), (100_000, 125_000), (40_000, 20_000),
+                                  (18_944, 3_000), (19_200, 70_000), (9_472, 500_000), (300, 6_000), (1_000_000, 4_096)])
+@pytest.mark.parametrize("k", [10, 32, 64])
+def test_filter_schedule_covers_every_unit_tile_pair_once(nq, n, k):
+    """The two-phase schedule (whole-corpus waves + split remainder) for the multi-GPU shard shapes and the edge shapes the GPU
+    tests do not reach: every (query unit, corpus tile) pair is scored by exactly one item, every split is non-empty, whole units
+    only ever write list 0, and the plan is never worse than the uniform split plan under the kernel's own cost model."""
+    from lotus_b200 import _native as nv
+    plan = nv.filter_plan(nq, n, k)
+    assert plan["kp"] > 0 and plan["n_splits"] >= 1
+    workers = 74 if plan["two_cta"] else 148
+    per_worker, n_units, n_ntiles = _schedule_items(plan, nq, n, workers)
+    assert plan["units_whole"] % workers == 0 and 0 <= plan["units_whole"] <= n_units
+    cover = np.zeros((n_units, n_ntiles), dtype=np.int32)
+    lists = set()
+    for items in per_worker:
+        for unit, split, t0, t1 in items:
+            assert t1 > t0, "empty split"
+            assert 0 <= split < plan["n_splits"]
+            cover[unit, t0:t1] += 1
+            assert (unit, split) not in lists
+            lists.add((unit, split))
+            if unit < plan["units_whole"]:
+                assert split == 0 and (t0, t1) == (0, n_ntiles)
+    assert (cover == 1).all()
+    # load balance: the busiest worker carries at most one item's worth of tiles more than the mean
+    loads = [sum(t1 - t0 for _, _, t0, t1 in items) for items in per_worker]
+    biggest_item = max(t1 - t0 for items in per_worker for _, _, t0, t1 in items)
+    assert max(loads) <= np.mean(loads) + biggest_item
+
+
+def test_sharded_hint_pruning_never_drops_a_global_topk_member():
+    """Host model of the two-stage row-sharded search: shard r reports lower_r = (its ceil(k/G)-th best FILTER score)
+    - eps; hint = min_r lower_r; a local row is re-scored only if filter + eps >= hint. With |filter - exact| <= eps the rows that
+    are pruned can never belong to (or tie with the k-th of) the merged exact top k — checked on random data with adversarial
+    filter noise at the full +-eps, including shards that hold none of the top k."""
+    rng = np.random.default_rng(0)
+    for trial in range(200):
+        G, k = int(rng.integers(2, 9)), int(rng.integers(1, 40))
+        sizes = rng.integers(max(1, k // G), 400, size=G)
+        eps = float(rng.choice([1e-4, 1e-2, 0.3]))
+        exact = [np.sort(rng.standard_normal(m))[::-1] * (1.0 if trial % 3 else 0.05) for m in sizes]
+        filt = [e + rng.choice([-eps, eps, 0.0], size=len(e)) * rng.random(len(e)) ** 0.2 for e in exact]
+        j = -(-k // G)
+        lowers = []
+        for f in filt:
+            top = np.sort(f)[::-1]
+            lowers.append(top[j - 1] - eps if len(top) >= j else -np.inf)
+        hint = min(lowers)
+        all_exact = np.concatenate(exact)
+        kth = np.sort(all_exact)[::-1][min(k, len(all_exact)) - 1]
+        for e, f in zip(exact, filt):
+            pruned = f + eps < hint
+            assert not (e[pruned] >= kth).any(), (trial, G, k, eps)
