@@ -187,6 +187,8 @@ B2_API int b2_kmeans_accumulate(b2_index* idx, const int64_t* ids, int64_t m, co
  * every x[i] was already bfloat16-representable, i.e. the 2-byte form loses nothing. The plugin uses it to ship query
  * vectors that came out of a bf16 index (faiss_vs.py:38-41 -> sem_sim_join.py:130-134) in their exact 2-byte form. */
 B2_API int b2_host_f32_to_bf16(const float* x, int64_t count, uint16_t* out, int32_t* all_exact);
+/* the exact inverse: out[i] = float32 value of the bfloat16 bit pattern x[i] (row gathers of a bf16 index, faiss_vs.py:38-41) */
+B2_API int b2_host_bf16_to_f32(const uint16_t* x, int64_t count, float* out);
 
 /* The filter kernel's work schedule for a shape (no device work; used by the CPU tests): kp = candidate-list capacity (0 = the
  * shape goes to the dense path), n_splits = corpus splits, units_whole = leading query units that sweep the whole corpus as one

@@ -20,7 +20,7 @@ SYMBOLS = [
     "b2_abi_version", "b2_last_error", "b2_device_count", "b2_max_k", "b2_index_create", "b2_index_free",
     "b2_index_ntotal", "b2_index_dim", "b2_index_dtype", "b2_index_metric", "b2_index_device", "b2_index_data_dev",
     "b2_index_search", "b2_index_search_dev", "b2_merge_topk_dev", "b2_index_search_packed_dev", "b2_merge_topk_packed_dev", "b2_index_search_stage1_dev", "b2_index_search_stage2_packed_dev", "b2_index_gather", "b2_threshold_pairs",
-    "b2_connected_components", "b2_kmeans", "b2_kmeans_assign", "b2_kmeans_accumulate", "b2_kmeans_assign_dev", "b2_kmeans_accumulate_dev", "b2_stats", "b2_stats_reset", "b2_last_filter_ms", "b2_host_f32_to_bf16", "b2_debug_filter_plan",
+    "b2_connected_components", "b2_kmeans", "b2_kmeans_assign", "b2_kmeans_accumulate", "b2_kmeans_assign_dev", "b2_kmeans_accumulate_dev", "b2_stats", "b2_stats_reset", "b2_last_filter_ms", "b2_host_f32_to_bf16", "b2_host_bf16_to_f32", "b2_debug_filter_plan",
 ]
 
 
@@ -90,6 +90,8 @@ def lib() -> ctypes.CDLL:
     L.b2_kmeans_accumulate_dev.argtypes = [vp, vp, i64, vp, i32, vp, vp, vp, vp, vp]
     L.b2_host_f32_to_bf16.restype = c.c_int
     L.b2_host_f32_to_bf16.argtypes = [vp, i64, vp, c.POINTER(i32)]
+    L.b2_host_bf16_to_f32.restype = c.c_int
+    L.b2_host_bf16_to_f32.argtypes = [vp, i64, vp]
     L.b2_debug_filter_plan.restype = c.c_int
     L.b2_debug_filter_plan.argtypes = [i64, i64, i32, i32, c.POINTER(i32), c.POINTER(i32), c.POINTER(i32), c.POINTER(i32)]
     L.b2_stats.restype = c.c_int
@@ -134,11 +136,14 @@ def stats_reset() -> None:
 
 
 # ---- bf16 helpers (numpy has no bfloat16: bit patterns travel as uint16) ------------------------------------------
-def f32_to_bf16_checked(a: np.ndarray) -> tuple[np.ndarray, bool]:
+def f32_to_bf16_checked(a: np.ndarray, out: "np.ndarray | None" = None) -> tuple[np.ndarray, bool]:
     """Round-to-nearest-even float32 -> bfloat16 bit patterns (uint16; NaN stays a quiet NaN) plus whether every value
-    was already bfloat16-representable. Host marshalling done by the library's threaded helper (no device work)."""
+    was already bfloat16-representable. Host marshalling done by the library's threaded helper (no device work). `out`: a
+    C-contiguous uint16 array of the same shape to write into (callers that convert a batch per call keep one: a fresh 150 MB
+    array costs more in page faults than the conversion itself)."""
     a = np.ascontiguousarray(a, dtype=np.float32)
-    out = np.empty(a.shape, dtype=np.uint16)
+    if out is None or out.shape != a.shape or out.dtype != np.uint16 or not out.flags.c_contiguous:
+        out = np.empty(a.shape, dtype=np.uint16)
     exact = ctypes.c_int32(0)
     check(lib().b2_host_f32_to_bf16(_ptr(a), a.size, _ptr(out), ctypes.byref(exact)))
     return out, bool(exact.value)
@@ -151,7 +156,11 @@ def f32_to_bf16_bits(a: np.ndarray) -> np.ndarray:
 
 def bf16_bits_to_f32(b: np.ndarray) -> np.ndarray:
     b = np.ascontiguousarray(b, dtype=np.uint16)
-    return (b.astype(np.uint32) << 16).view(np.float32).reshape(b.shape)
+    if b.size < (1 << 18):
+        return (b.astype(np.uint32) << 16).view(np.float32).reshape(b.shape)
+    out = np.empty(b.shape, dtype=np.float32)
+    check(lib().b2_host_bf16_to_f32(_ptr(b), b.size, _ptr(out)))
+    return out
 
 
 def _ptr(a: Optional[np.ndarray]):

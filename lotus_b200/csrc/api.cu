@@ -638,6 +638,33 @@ int b2_host_f32_to_bf16(const float* x, int64_t count, uint16_t* out, int32_t* a
     return B2_OK;
 }
 
+// Host-side marshalling helper: bf16 bit patterns -> float32 (exact), threaded.
+int b2_host_bf16_to_f32(const uint16_t* x, int64_t count, float* out) {
+    if (count < 0 || (count > 0 && (!x || !out))) { set_error("bad conversion arguments"); return B2_EINVAL; }
+    const int64_t kChunk = 1 << 20;
+    const int64_t nchunks = (count + kChunk - 1) / kChunk;
+    unsigned hw = std::thread::hardware_concurrency();
+    const int nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(hw ? hw : 1, 16), nchunks));
+    std::atomic<int64_t> next{0};
+    auto work = [&]() {
+        uint32_t* o = reinterpret_cast<uint32_t*>(out);
+        for (;;) {
+            const int64_t c = next.fetch_add(1);
+            if (c >= nchunks) break;
+            const int64_t lo = c * kChunk, hi = std::min(count, lo + kChunk);
+            for (int64_t i = lo; i < hi; ++i) o[i] = (uint32_t)x[i] << 16;
+        }
+    };
+    if (nthreads <= 1) {
+        work();
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; ++t) pool.emplace_back(work);
+        for (auto& t : pool) t.join();
+    }
+    return B2_OK;
+}
+
 // The filter's work schedule for a (queries, rows, k) shape on `num_sms` SMs — no device work: lets the CPU test-suite check that
 // every (query unit, corpus tile) pair is covered exactly once for the shapes the GPU tests do not reach.
 int b2_debug_filter_plan(int64_t nq, int64_t n, int32_t k, int32_t num_sms, int32_t* kp, int32_t* n_splits, int32_t* units_whole,

@@ -77,7 +77,7 @@ class BF16Backed(np.ndarray):
         return np.ascontiguousarray(f32, dtype=np.float32).view(BF16Backed)
 
 
-def _to_host_matrix(a: Any, want_bf16: bool, exact_bf16_ok: bool = False):
+def _to_host_matrix(a: Any, want_bf16: bool, exact_bf16_ok: bool = False, scratch: "dict | None" = None):
     """-> (array for the C-ABI, native dtype code, float32 view of the stored values).
     exact_bf16_ok: when every float32 value is bfloat16-representable (e.g. vectors fetched from a bf16 index,
     sem_sim_join.py:112-118 -> :130-134) ship the exact 2-byte patterns instead: half the H2D bytes and the exact-operand
@@ -99,7 +99,13 @@ def _to_host_matrix(a: Any, want_bf16: bool, exact_bf16_ok: bool = False):
         bits = nv.f32_to_bf16_bits(f)
         return bits, nv.BF16, nv.bf16_bits_to_f32(bits)
     if exact_bf16_ok and f.size:
-        bits, exact = nv.f32_to_bf16_checked(f)
+        buf = None
+        if scratch is not None:  # one reusable staging array per store (the C call copies it to the device before returning)
+            buf = scratch.get("q16")
+            if buf is None or buf.size < f.size:
+                buf = scratch["q16"] = np.empty(f.size, dtype=np.uint16)
+            buf = buf[:f.size].reshape(f.shape)
+        bits, exact = nv.f32_to_bf16_checked(f, out=buf)
         if exact:
             return bits, nv.BF16, f
     return f, nv.F32, f
@@ -214,6 +220,7 @@ class B200VS(VS):
         self.vecs: Any = None
         self._cache: "OrderedDict[str, tuple[float, nv.Index, Any]]" = OrderedDict()
         self._cache_size = max(2, cache_size)
+        self._scratch: dict = {}
 
     # -- index lifetime ---------------------------------------------------------------------------------------------
     def _build(self, embeddings: Any) -> nv.Index:
@@ -315,7 +322,7 @@ class B200VS(VS):
         t = _cuda_tensor(query_vectors)
         if t is not None and ids_a is None and t.dim() == 2 and t.device.index == self.device and not isinstance(self.b2_index, MultiDeviceIndex):
             return self._call_device(t, int(K))
-        q, code, _ = _to_host_matrix(query_vectors, False, exact_bf16_ok=self.b2_index.dtype == nv.BF16)
+        q, code, _ = _to_host_matrix(query_vectors, False, exact_bf16_ok=self.b2_index.dtype == nv.BF16, scratch=self._scratch)
         if q.shape[1] != self.b2_index.d:
             raise ValueError(f"query dimension {q.shape[1]} does not match the index dimension {self.b2_index.d}")
         try:
