@@ -34,6 +34,8 @@ with tempfile.TemporaryDirectory() as tmp:
 
     print(papers.sem_sim_join(topics, left_on="title", right_on="topic", K=1))         # kNN join, one topic per paper
     print(papers.sem_search("title", "wild yeast bread", K=2, return_scores=True))     # top-K rows for one query
+    for q, hits in zip(["wild yeast bread", "gpu kernels"], papers.sem_search("title", ["wild yeast bread", "gpu kernels"], K=1)):
+        print(q, "->", hits["title"].tolist())                                          # several queries, ONE device search
     print(papers.sem_dedup("title", threshold=0.9))                                    # near-duplicate titles collapse
     print(papers.sem_cluster_by("title", 2))                                           # faiss-parity k-means, cluster_id column
     parts = papers.sem_partition_by(lotus.utils.cluster("title", 2))                   # same clustering as a partitioner

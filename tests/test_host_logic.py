@@ -523,3 +523,55 @@ def test_sharded_hint_pruning_never_drops_a_global_topk_member():
         for e, f in zip(exact, filt):
             pruned = f + eps < hint
             assert not (e[pruned] >= kth).any(), (trial, G, k, eps)
+
+
+class _PlainVS(NumpyVS):
+    """A store WITHOUT the streaming extensions (what the reference's FaissVS looks like to the accessors)."""
+    threshold_pairs = property(lambda self: (_ for _ in ()).throw(AttributeError("no threshold_pairs")))
+    kmeans = property(lambda self: (_ for _ in ()).throw(AttributeError("no kmeans")))
+
+
+def test_accessors_fall_back_to_the_reference_flow_for_stores_without_extensions(env, monkeypatch):
+    """ADVICE r1 (sem_dedup.py:55): with a VS that has neither threshold_pairs nor kmeans the accessors must follow the reference's
+    own control flow — sem_dedup through vs(q, K=n, ids=rows) (sem_dedup.py:45 via sem_sim_join.py:132-134), cluster through
+    faiss.Kmeans (utils.py:59-70) — instead of raising; and missing text values never join a component."""
+    import sys
+    import types
+    import lotus_b200.sem_ops.sem_dedup as sd
+    rm, vs, tmp = env
+    monkeypatch.setattr(sd.nv, "connected_components", lambda n, pi, pj, device=0: oracle.connected_components(n, pi, pj))
+    vals = [f"v{i % 12}" for i in range(40)] + [None, None]
+    df = pd.DataFrame({"Text": vals}).sem_index("Text", str(tmp / "dd"))
+    want = df.sem_dedup("Text", threshold=0.3)               # streaming path of the oracle-backed test double
+    plain = _PlainVS()
+    plain.dirs, plain.index_dir, plain.x = vs.dirs, vs.index_dir, vs.x
+    assert not hasattr(plain, "threshold_pairs") and not hasattr(plain, "kmeans")
+    lotus.settings.configure(vs=plain)
+    got = df.sem_dedup("Text", threshold=0.3)                # reference flow: vs(q, K=n, ids=rows) + `_scores > threshold`
+    assert got["Text"].tolist() == want["Text"].tolist()
+    assert got["Text"].isna().sum() == 2                      # None never equals anything: both rows survive
+    # cluster: faiss.Kmeans stand-in (what the reference calls, utils.py:61-65)
+    calls = {}
+    fake = types.ModuleType("faiss")
+
+    class Kmeans:
+        def __init__(self, d, k, niter=25, verbose=False):
+            calls["args"] = (d, k, niter, verbose)
+
+        def train(self, x):
+            self.x = np.asarray(x, dtype=np.float32)
+            _, self.cent, _ = oracle.kmeans(self.x, calls["args"][1], niter=calls["args"][2])
+            outer = self
+
+            class Ix:
+                def search(self, q, kk):
+                    return oracle.knn(outer.cent, np.asarray(q, dtype=np.float32), kk, oracle.L2)
+            self.index = Ix()
+
+    fake.Kmeans = Kmeans
+    monkeypatch.setitem(sys.modules, "faiss", fake)
+    cdf = pd.DataFrame({"t": [f"doc{i}" for i in range(30)]}).sem_index("t", str(tmp / "cc"))
+    plain.dirs = vs.dirs
+    out = cdf.sem_cluster_by("t", 3, niter=4)
+    a, _, _ = oracle.kmeans(rm(cdf["t"].tolist()), 3, niter=4)
+    assert calls["args"][1:3] == (3, 4) and out["cluster_id"].tolist() == a.tolist()
