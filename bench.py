@@ -357,9 +357,11 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": "sem_sim_join queries/sec (1M x 768, K=32)", "value": val, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (bf16 values)", "data": "synthetic",
+        # same keys and workload string as the B200 arm's `config`; what is specific to this run sits in `reference_run`
         "config": {"workload": f"sem_sim_join {args.nq} queries x {n} index, {d}-d bf16, K={k} (BASELINE.json configs[2])", "nq": args.nq,
-                   "n": n, "d": d, "k": k, "sample_queries_per_step": sample, "datagen_s": round(gen_s, 1),
-                   "tflops": 2.0 * n * d * val / 1e12},
+                   "n": n, "d": d, "k": k, "parallelism": f"{arms['cores']} host threads (no GPU)", "l2_policy": "n/a (CPU arm)"},
+        "reference_run": {"sample_queries_per_step": sample, "datagen_s": round(gen_s, 1), "tflops": 2.0 * n * d * val / 1e12,
+                          "data": "same generator, distribution and seeds as the B200 arm (numpy stream instead of the CUDA one)"},
         "cpu_baseline": arms, "oracle": probe,
         "e2e": {"value": val, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "operator_e2e": op,
